@@ -1,0 +1,79 @@
+// casq_b200: on-device envelope sampler (device functions shared by the stand-alone sampler kernel and
+// by every stepper, which evaluates the envelope on the fly when the sample index changes).
+//
+// Families = the qiskit.pulse.library classes casq's gates forward to (src/casq/gates/*_pulse_gate.py);
+// formulas per SURVEY.md Appendix A.2: midpoint sampling samples[n] = envelope(n + 1/2),
+// lifted(t; mu, t0, sigma) = (g(t) - g(t0)) / (1 - g(t0)), g(x) = exp(-((x-mu)/sigma)^2 / 2).
+#pragma once
+#include "common.cuh"
+
+struct dcplx {
+  double re, im;
+};
+
+__device__ __forceinline__ double casq_lifted(double t, double mu, double t_zero, double inv_sigma) {
+  double a = (t - mu) * inv_sigma;
+  double b = (t_zero - mu) * inv_sigma;
+  double g = exp(-0.5 * a * a);
+  double off = exp(-0.5 * b * b);
+  return (g - off) / (1.0 - off);
+}
+
+// envelope(n + 1/2) for local sample n in [0, duration); params = (amp, angle, sigma, width, beta)
+__device__ __forceinline__ dcplx casq_envelope_eval(int kind, int duration, int n, double amp, double angle,
+                                                    double sigma, double width, double beta) {
+  double sa, ca;
+  sincos(angle, &sa, &ca);
+  const double t = (double)n + 0.5;
+  const double c = 0.5 * (double)duration;
+  double er = 1.0, ei = 0.0;
+  if (kind == CASQ_PULSE_GAUSSIAN || kind == CASQ_PULSE_DRAG) {
+    const double inv_s = 1.0 / sigma;
+    const double g = casq_lifted(t, c, (double)duration + 1.0, inv_s);
+    er = g;
+    if (kind == CASQ_PULSE_DRAG) ei = beta * (-(t - c) * inv_s * inv_s) * g;
+  } else if (kind == CASQ_PULSE_GAUSSIAN_SQUARE || kind == CASQ_PULSE_GAUSSIAN_SQUARE_DRAG) {
+    const double inv_s = 1.0 / sigma;
+    const double tl = c - 0.5 * width, tr = c + 0.5 * width;
+    if (t <= tl) {
+      const double g = casq_lifted(t, tl, -1.0, inv_s);
+      er = g;
+      if (kind == CASQ_PULSE_GAUSSIAN_SQUARE_DRAG) ei = beta * (-(t - tl) * inv_s * inv_s) * g;
+    } else if (t >= tr) {
+      const double g = casq_lifted(t, tr, (double)duration + 1.0, inv_s);
+      er = g;
+      if (kind == CASQ_PULSE_GAUSSIAN_SQUARE_DRAG) ei = beta * (-(t - tr) * inv_s * inv_s) * g;
+    }
+  }
+  dcplx out;
+  const double ar = amp * ca, ai = amp * sa;
+  out.re = ar * er - ai * ei;
+  out.im = ar * ei + ai * er;
+  return out;
+}
+
+// Slots as the kernels see them: `channel` already remapped to the ACTIVE channel index.
+struct DevSlots {
+  int n;
+  int kind[CASQ_MAX_SLOTS], ach[CASQ_MAX_SLOTS], start[CASQ_MAX_SLOTS], duration[CASQ_MAX_SLOTS];
+};
+
+// Sum of all slots playing on each active channel at global sample `gidx` for batch point b.
+template <int KA>
+__device__ __forceinline__ void casq_channel_envelopes(const DevSlots& s, const double* __restrict__ params,
+                                                       long long B, long long b, int gidx, dcplx* env) {
+#pragma unroll
+  for (int k = 0; k < KA; k++) env[k].re = env[k].im = 0.0;
+  for (int i = 0; i < s.n; i++) {
+    const int n = gidx - s.start[i];
+    if (n < 0 || n >= s.duration[i]) continue;
+    const double* p = params + (long long)i * CASQ_NPARAM * B + b;
+    dcplx e = casq_envelope_eval(s.kind[i], s.duration[i], n, p[0], p[B], p[2 * B], p[3 * B], p[4 * B]);
+#pragma unroll
+    for (int k = 0; k < KA; k++)
+      if (s.ach[i] == k) {
+        env[k].re += e.re;
+        env[k].im += e.im;
+      }
+  }
+}

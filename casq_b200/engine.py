@@ -1,0 +1,135 @@
+"""Batched device solves: thin torch-tensor wrappers over the C ABI (include/casq_b200.h).
+
+PyTorch is the host container only (device memory, streams); all arithmetic happens in libcasq_b200.so.
+Every function raises CasqError when CUDA or the library is unavailable -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+from .common.exceptions import CasqError
+
+PARAM_ORDER = ("amp", "angle", "sigma", "width", "beta")
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise CasqError("casq_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", device if isinstance(device, int) else (device.index or 0))
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def pack_params(slot_params: Sequence[dict], batch: Optional[int] = None, device=None, pin: bool = False) -> torch.Tensor:
+    """Build the SoA parameter block [n_slots, 5, B] (float64) from per-slot dicts.
+
+    Each dict maps amp/angle/sigma/width/beta to a scalar or a length-B array; missing entries are 0
+    (angle None -> 0, like qiskit's symbolic pulses).  Returned on `device` when given, else on the host
+    (pinned when `pin`).
+    """
+    B = batch
+    for p in slot_params:
+        for v in p.values():
+            if v is not None and np.ndim(v) > 0:
+                n = len(v)
+                if B is not None and B != n and B != 1:
+                    raise CasqError(f"inconsistent batch sizes in pulse parameters: {B} vs {n}")
+                B = n if (B is None or B == 1) else B
+    B = 1 if B is None else B
+    host = torch.zeros((max(1, len(slot_params)), _native.NPARAM, B), dtype=torch.float64, pin_memory=pin)
+    hv = host.numpy()
+    for s, p in enumerate(slot_params):
+        unknown = set(p) - set(PARAM_ORDER)
+        if unknown:
+            raise CasqError(f"unknown pulse parameter(s): {sorted(unknown)}")
+        for j, name in enumerate(PARAM_ORDER):
+            v = p.get(name)
+            if v is None:
+                continue
+            hv[s, j, :] = np.asarray(v, dtype=np.float64)
+    return host if device is None else host.to(device, non_blocking=True)
+
+
+def envelope_sample(kind, duration: int, params: torch.Tensor) -> torch.Tensor:
+    """samples[b, n] = envelope(n + 1/2) on the device.  params: CUDA float64 [5, B] (one slot)."""
+    if not params.is_cuda:
+        raise CasqError("envelope_sample: params must be a CUDA tensor")
+    params = params.contiguous()
+    if params.dim() != 2 or params.shape[0] != _native.NPARAM or params.dtype != torch.float64:
+        raise CasqError("envelope_sample: params must be float64 [5, B]")
+    B = params.shape[1]
+    out = torch.empty((B, duration), dtype=torch.complex128, device=params.device)
+    k = _native.PULSE_KINDS[kind] if isinstance(kind, str) else int(kind)
+    with torch.cuda.device(params.device):
+        _native.check(
+            _native.load().casq_envelope_sample(k, int(duration), B, params.data_ptr(), out.data_ptr(), _stream_ptr(params.device)),
+            "casq_envelope_sample",
+        )
+    return out
+
+
+def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_span, max_dt: float,
+                 t_eval=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fixed-step RK4 for a batch of pulse points.  Returns CUDA complex128 [B, T, d]: the states
+    Solver.solve returns (rotating frame, lab basis) at t_eval (or at the two ends of t_span).
+
+    slots: [(kind, channel_index, start, duration)]; params: CUDA float64 [n_slots, 5, B];
+    y0: [d] or [B, d] (numpy or torch, lab basis).
+    """
+    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
+    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
+        raise CasqError("solve_sv_rk4: params must be a CUDA float64 tensor [n_slots, 5, B]")
+    params = params.contiguous()
+    slots = list(slots)
+    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
+        raise CasqError(f"solve_sv_rk4: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
+    B = params.shape[2]
+    d = model.dim
+    y0_t = torch.as_tensor(np.asarray(y0) if not isinstance(y0, torch.Tensor) else y0).to(torch.complex128)
+    if y0_t.shape not in ((d,), (B, d)):
+        raise CasqError(f"solve_sv_rk4: y0 must be [{d}] or [{B},{d}], got {tuple(y0_t.shape)}")
+    y0_t = y0_t.to(dev).contiguous()
+    if t_eval is None:
+        T, te_ptr, te = 2, None, None
+    else:
+        te = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+        T, te_ptr = len(te), te.ctypes.data
+    if out is None:
+        out = torch.empty((B, T, d), dtype=torch.complex128, device=dev)
+    elif out.shape != (B, T, d) or out.dtype != torch.complex128 or not out.is_cuda or not out.is_contiguous():
+        raise CasqError("solve_sv_rk4: bad `out` tensor")
+    with torch.cuda.device(dev):
+        _native.check(
+            _native.load().casq_solve_sv_rk4(
+                model.handle, len(slots), _native.make_slots(slots), B, params.data_ptr(), y0_t.data_ptr(),
+                1 if y0_t.dim() == 2 else 0, float(t_span[0]), float(t_span[1]), float(max_dt), T, te_ptr,
+                out.data_ptr(), _stream_ptr(dev)),
+            "casq_solve_sv_rk4",
+        )
+    return out
+
+
+def fp64_fma_probe(device=0, iters: int = 4096, reps: int = 5) -> float:
+    """Measured fp64 FMA throughput (TFLOP/s) of this GPU: the roofline denominator for the RK4 kernel."""
+    dev = _require_cuda(device)
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    props = torch.cuda.get_device_properties(dev)
+    grid, block = props.multi_processor_count * 8, 256
+    lib = _native.load()
+    best = 0.0
+    with torch.cuda.device(dev):
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _native.check(lib.casq_fp64_fma_probe(grid, block, iters, sink.data_ptr(), _stream_ptr(dev)), "casq_fp64_fma_probe")
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = max(best, 2.0 * 16 * iters * grid * block / (ms * 1e-3) / 1e12)
+    return best
