@@ -31,9 +31,13 @@ _SIGNATURES = {
     "casq_model_set_dissipators": (C.c_int, [_P, C.c_int, _P]),
     "casq_model_get": (C.c_int, [_P, _P, _P, _P, _P]),
     "casq_model_dim": (C.c_int, [_P]),
+    "casq_model_invalidate_cache": (C.c_int, [_P]),
     "casq_envelope_sample": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
     "casq_solve_sv_rk4": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,
                                     C.c_double, C.c_int, _P, _P, _P]),
+    "casq_solve_sv_dopri5": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,
+                                       C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
+    "casq_postprocess_sv": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "casq_fp64_fma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
 }
 
@@ -116,6 +120,9 @@ class NativeModel:
     def set_dissipators(self, ops) -> None:
         ops = _c128(ops).reshape(-1, self.dim, self.dim)
         check(load().casq_model_set_dissipators(self.handle, ops.shape[0], ops.ctypes.data), "casq_model_set_dissipators")
+
+    def invalidate_cache(self) -> None:
+        check(load().casq_model_invalidate_cache(self.handle), "casq_model_invalidate_cache")
 
     def close(self) -> None:
         if getattr(self, "handle", None):

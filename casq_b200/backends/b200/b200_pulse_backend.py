@@ -1,0 +1,266 @@
+"""B200 pulse backend: casq's PulseBackend API on top of the sm_100a engine.
+
+Plays the role QiskitPulseBackend plays in casq (src/casq/backends/qiskit/qiskit_pulse_backend.py:45-189):
+``_get_native_backend`` builds the engine model where casq builds ``Solver`` + ``DynamicsBackendPatch``
+(:166-189); ``solve`` packs options, runs ONE circuit and converts the result (:119-164) with the
+post-processing semantics of ``get_experiment_result`` (src/casq/backends/qiskit/helpers.py:98-162).
+``solve_batch`` is the additive API: the same path for B pulse-parameter points in one launch (casq has no
+sweep API; a sweep there is a Python loop of ``solve`` calls).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from datetime import datetime
+from typing import Any, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from ... import engine
+from ..._native import NativeModel
+from ...common.exceptions import CasqError
+from ...gates.pulse_circuit import PulseCircuit
+from ...gates.pulse_gate import PulseGate
+from ...models.control_model import ControlModel
+from ...models.hamiltonian_model import HamiltonianModel
+from ...pulse import Play, Schedule
+from ...quantum_info import DensityMatrix, Statevector
+from ..pulse_backend import PulseBackend
+
+_FIXED = ("RK4", "jax_RK4")
+_SCIPY = ("BDF", "DOP853", "Radau", "RK23", "RK45")
+
+
+@dataclass
+class BatchSolution:
+    """Result of ``solve_batch``: device tensors for B pulse points at T time points.
+
+    states are lab-frame, dressed-basis, normalised (helpers.py:100-109); populations[..., 0/1] are casq's
+    {"0","1"} with every level >= 1 folded into "1" (helpers.py:129-134); probabilities are per level.
+    """
+
+    times: np.ndarray
+    states: torch.Tensor
+    probabilities: torch.Tensor
+    populations: torch.Tensor
+    raw: Optional[torch.Tensor] = None
+    nsteps: Optional[torch.Tensor] = None
+    status: Optional[torch.Tensor] = None
+
+    @property
+    def batch_size(self) -> int:
+        return int(self.states.shape[0])
+
+
+class B200PulseBackend(PulseBackend):
+    """PulseBackend whose ``solve`` runs on a B200 through libcasq_b200.so (no CPU fallback)."""
+
+    def __init__(self, hamiltonian: HamiltonianModel, control: ControlModel, seed: Optional[int] = None, device: int = 0):
+        self._device = int(device)
+        super().__init__(hamiltonian=hamiltonian, control=control, seed=seed)
+
+    # ------------------------------------------------------------------ construction
+    def _get_native_backend(self) -> NativeModel:
+        freqs = self.control.channel_carrier_freqs or {}
+        missing = [c for c in self.hamiltonian.channels if c not in freqs]
+        if missing:
+            raise CasqError(f"ControlModel.channel_carrier_freqs has no entry for channel(s) {missing}.")
+        return NativeModel(
+            static=self.hamiltonian.static_operator,
+            operators=self.hamiltonian.operators,
+            carrier_hz=[freqs[c] for c in self.hamiltonian.channels],
+            dt=self.control.dt,
+            rotating_frame=self.hamiltonian.rotating_frame,
+            rwa_cutoff_freq=self.hamiltonian.rwa_cutoff_freq,
+            device=self._device,
+        )
+
+    @property
+    def native(self) -> NativeModel:
+        return self._native_backend
+
+    @property
+    def dim(self) -> int:
+        return self._native_backend.dim
+
+    def ground_state(self) -> np.ndarray:
+        """Column 0 of the dressed eigenbasis: what ``initial_state=None`` means."""
+        return np.array(self._native_backend.dressed_states[:, 0])
+
+    # ------------------------------------------------------------------ schedule handling
+    def _circuit_to_schedule(self, circuit: PulseCircuit):
+        """ASAP-schedule the calibrated gates; returns (Schedule, t_acquire in samples, measured qubits)."""
+        cursor: dict = {}
+        sched = Schedule(name=circuit.name)
+        acquire_times = []
+        measured = []
+        for inst in circuit.data:
+            if inst.operation == "measure":
+                q = inst.qubits[0]
+                acquire_times.append(cursor.get(q, 0))
+                measured.append(q)
+                continue
+            gate = inst.operation
+            cal = circuit.calibrations.get(gate.name, {}).get((tuple(inst.qubits), ()))
+            if cal is None:
+                raise CasqError(f"Gate '{gate.name}' on qubits {inst.qubits} has no pulse calibration.")
+            start = max(cursor.get(q, 0) for q in inst.qubits)
+            for s, sub in cal.instructions:
+                sched.insert(start + s, sub)
+            for q in inst.qubits:
+                cursor[q] = start + cal.duration
+        if not acquire_times:
+            raise CasqError("At least one measurement must be present in the circuit (DynamicsBackend requires an acquire).")
+        if len(set(acquire_times)) > 1:
+            t_acq = max(acquire_times)  # measurements are aligned to the latest one
+        else:
+            t_acq = acquire_times[0]
+        if t_acq <= 0:
+            raise CasqError("The circuit has no pulse before its measurement: nothing to simulate.")
+        return sched, t_acq, measured
+
+    def _slots_from_schedule(self, sched: Schedule):
+        slots, params = [], []
+        for start, inst in sched.plays():
+            name = inst.channel.name
+            if name not in self.hamiltonian.channels:
+                raise CasqError(f"Schedule plays on channel '{name}' which is not in the Hamiltonian model {self.hamiltonian.channels}.")
+            slots.append((inst.pulse.kind, self.hamiltonian.channels.index(name), start, inst.pulse.duration))
+            params.append(inst.pulse.engine_params())
+        if len(slots) > 4:
+            raise CasqError(f"At most 4 Play instructions per schedule are supported, got {len(slots)}.")
+        return slots, params
+
+    # ------------------------------------------------------------------ core batched run
+    def _run(self, slots, params_dev, y0, t_span, method: str, t_eval, options: dict):
+        model = self._native_backend
+        nsteps = status = None
+        if method in _FIXED:
+            if "max_dt" not in options:
+                raise CasqError(f"Method '{method}' is a fixed-step solver and needs run_options['max_dt'].")
+            raw = engine.solve_sv_rk4(model, slots, params_dev, y0, t_span, options["max_dt"], t_eval)
+        elif method == "jax_odeint" or method in _SCIPY:
+            # scipy-named adaptive methods run on the device Dopri5 as well.  casq passes no tolerances, so the
+            # reference runs them at scipy's rtol=1e-3 (SURVEY §3.1 "accuracy trap"); here an unset tolerance
+            # means 1.4e-8 (the jax_odeint default), i.e. closer to the true solution than the reference.
+            raw, nsteps, status = engine.solve_sv_dopri5(
+                model, slots, params_dev, y0, t_span,
+                rtol=options.get("rtol", 1.4e-8), atol=options.get("atol", 1.4e-8),
+                hmax=options.get("hmax", options.get("max_step", 0.0)), mxstep=options.get("mxstep", 0),
+                t_eval=t_eval, return_stats=True)
+        elif method == "LSODA":
+            raise CasqError("SCIPY_LSODA cannot integrate complex states (scipy limitation in the reference too).")
+        else:
+            raise CasqError(f"Unknown ODE solver method '{method}'.")
+        return raw, nsteps, status
+
+    def solve_slots_batch(self, slots: Sequence[tuple], slot_params: Sequence[dict], t_final: int, method: str = "RK4",
+                          initial_state=None, steps: Optional[int] = None, run_options: Optional[dict] = None,
+                          keep_raw: bool = False, params_device: Optional[torch.Tensor] = None) -> BatchSolution:
+        """Lowest-level batched entry: explicit slots [(kind, channel_index, start, duration)] and per-slot
+        parameter dicts (scalars or length-B arrays), t_span = [0, t_final*dt]."""
+        options = dict(run_options or {})
+        options.pop("method", None)
+        dev = torch.device("cuda", self._device)
+        if params_device is None:
+            if not torch.cuda.is_available():
+                raise CasqError("casq_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+            params_device = engine.pack_params(slot_params, device=dev)
+        t_span = (0.0, float(t_final) * self.control.dt)
+        t_eval = None if steps is None else np.linspace(t_span[0], t_span[1], int(steps))
+        y0 = self.ground_state() if initial_state is None else np.asarray(getattr(initial_state, "data", initial_state))
+        if y0.ndim == 2 and y0.shape == (self.dim, self.dim):
+            raise CasqError("DensityMatrix initial states need the Lindblad path (solve_lindblad_batch).")
+        raw, nsteps, status = self._run(slots, params_device, y0, t_span, method, t_eval, options)
+        times = np.asarray(t_span) if t_eval is None else t_eval
+        states, probs, pops = engine.postprocess_sv(self._native_backend, times, raw)
+        return BatchSolution(times=times, states=states, probabilities=probs, populations=pops,
+                             raw=raw if keep_raw else None, nsteps=nsteps, status=status)
+
+    def solve_batch(self, gate: PulseGate, parameters: Union[dict, np.ndarray], method: "PulseBackend.ODESolverMethod",
+                    qubit: int = 0, amplitude=None, angle=None, initial_state=None, steps: Optional[int] = None,
+                    run_options: Optional[dict] = None, keep_raw: bool = False) -> BatchSolution:
+        """Sweep / candidate batch for one gate: ``parameters`` is a dict of arrays (e.g. {"sigma": [B],
+        "beta": [B]}) or a [B, P] array in ``gate.to_parameters_dict`` order; ``amplitude``/``angle`` may be
+        arrays too (default: the gate's own).  Reduces to ``solve`` semantics for B = 1."""
+        if not isinstance(parameters, dict):
+            arr = np.atleast_2d(np.asarray(parameters, dtype=float))
+            parameters = gate.to_parameters_dict(arr.T)
+        amp = gate.amplitude if amplitude is None else amplitude
+        ang = gate.angle if angle is None else angle
+        pulse = type(gate.pulse({k: np.asarray(v, dtype=float) for k, v in parameters.items()}))(
+            duration=gate.duration, amp=np.asarray(amp, dtype=float), angle=0.0 if ang is None else np.asarray(ang, dtype=float),
+            limit_amplitude=gate.limit_amplitude, name=gate.name, **{k: np.asarray(v, dtype=float) for k, v in parameters.items()})
+        name = f"d{qubit}"
+        if name not in self.hamiltonian.channels:
+            raise CasqError(f"DriveChannel({qubit}) ('{name}') is not in the Hamiltonian model {self.hamiltonian.channels}.")
+        slots = [(pulse.kind, self.hamiltonian.channels.index(name), 0, pulse.duration)]
+        m = method.value if isinstance(method, PulseBackend.ODESolverMethod) else str(method)
+        return self.solve_slots_batch(slots, [pulse.engine_params()], pulse.duration, m, initial_state, steps,
+                                      run_options, keep_raw)
+
+    # ------------------------------------------------------------------ the drop-in call
+    def solve(
+        self,
+        circuit: PulseCircuit,
+        method: "PulseBackend.ODESolverMethod",
+        initial_state: Optional[Union[DensityMatrix, Statevector]] = None,
+        shots: int = 1024,
+        steps: Optional[int] = None,
+        run_options: Optional[dict[str, Any]] = None,
+    ) -> "PulseBackend.Solution":
+        """Same contract as QiskitPulseBackend.solve (qiskit_pulse_backend.py:119-164).
+
+        The enum ``method`` wins over run_options["method"] (:147-150); ``initial_state=None`` is the dressed
+        ground state; ``steps`` gives that many evenly spaced time points including both ends
+        (dynamics_backend_patch.py:180-184), otherwise the two end points are returned.
+        """
+        if run_options:
+            run_options.update(method=method.value)
+        else:
+            run_options = {"method": method.value}
+        sched, t_acq, measured = self._circuit_to_schedule(circuit)
+        slots, params = self._slots_from_schedule(sched)
+        batch = self.solve_slots_batch(slots, params, t_acq, method.value, initial_state, steps, run_options)
+        if batch.status is not None and int(batch.status[0].item()) != 0:
+            raise CasqError(f"Adaptive solve failed for this circuit (status {int(batch.status[0].item())}).")
+        states = batch.states[0].cpu().numpy()
+        probs = batch.probabilities[0].cpu().numpy()
+        return self._to_solution(circuit.name, batch.times, states, probs, shots, measured)
+
+    def _to_solution(self, name, times, states, probs, shots, measured) -> "PulseBackend.Solution":
+        """get_experiment_result + convert_to_solution (helpers.py:58-230) for one experiment."""
+        d = self.dim
+        rng = np.random.default_rng(self._seed)
+        seed = int(rng.integers(low=0, high=9223372036854775807))
+        theta = 2 * np.pi / d
+        centers = np.array([[np.cos(i * theta), np.sin(i * theta)] for i in range(d)])
+        out_states, pops_l, samples_l, counts_l, iq_l, avg_l = [], [], [], [], [], []
+        for t in range(len(times)):
+            out_states.append(Statevector(states[t], dims=(d,)))
+            p = np.clip(probs[t], 0.0, None)
+            pop = {}
+            if p[0] > 0:
+                pop["0"] = float(p[0])
+            if p[1:].sum() > 0:
+                pop["1"] = float(p[1:].sum())
+            pops_l.append(pop)
+            keys = list(pop.keys())
+            pv = np.array([pop[k] for k in keys])
+            smp = np.random.default_rng(seed).choice(keys, size=shots, p=pv / pv.sum())
+            samples_l.append(smp.tolist())
+            vals, cnts = np.unique(smp, return_counts=True)
+            counts_l.append({str(v): int(c) for v, c in zip(vals, cnts)})
+            # IQ cloud: multinomial over levels, Gaussian blobs of width 0.2 around the level centres
+            rng_iq = np.random.default_rng(seed)
+            n_lvl = rng_iq.multinomial(shots, p / p.sum())
+            pts_i = np.concatenate([rng_iq.normal(centers[i, 0], 0.2, n) for i, n in enumerate(n_lvl)])
+            pts_q = np.concatenate([rng_iq.normal(centers[i, 1], 0.2, n) for i, n in enumerate(n_lvl)])
+            iq = 2 * np.stack([pts_i, pts_q], axis=1)
+            iq_l.append([(float(a), float(b)) for a, b in iq])
+            avg = iq.mean(axis=0)
+            avg_l.append((float(avg[0]), float(avg[1])))
+        return PulseBackend.Solution(
+            circuit_name=name, qubits=[0], times=np.asarray(times), samples=samples_l, counts=counts_l,
+            populations=pops_l, states=out_states, iq_data=iq_l, avg_iq_data=avg_l, shots=shots, seed=seed,
+            is_success=True, timestamp=datetime.timestamp(datetime.now()))

@@ -26,8 +26,9 @@ __global__ void envelope_sample_kernel(int kind, int duration, long long B, cons
 extern "C" int casq_envelope_sample(int kind, int duration, int64_t B, const double* params_dev, double* out_dev,
                                     void* stream) {
   if (kind < 0 || kind > CASQ_PULSE_GAUSSIAN_SQUARE_DRAG) CASQ_FAIL(CASQ_ERR_INVALID, "unknown pulse kind %d", kind);
-  if (duration < 1 || B < 0 || !params_dev || !out_dev) CASQ_FAIL(CASQ_ERR_INVALID, "casq_envelope_sample: bad arguments");
+  if (duration < 1 || B < 0) CASQ_FAIL(CASQ_ERR_INVALID, "casq_envelope_sample: bad arguments");
   if (B == 0) return CASQ_OK;
+  if (!params_dev || !out_dev) CASQ_FAIL(CASQ_ERR_INVALID, "casq_envelope_sample: NULL buffer");
   const long long n = (long long)B * duration;
   envelope_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, duration, B, params_dev,
                                                                                        out_dev);

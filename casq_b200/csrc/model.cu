@@ -283,6 +283,12 @@ extern "C" int casq_model_set_dissipators(casq_model* m, int n, const double* op
 
 extern "C" int casq_model_dim(const casq_model* m) { return m ? m->d : CASQ_ERR_INVALID; }
 
+extern "C" int casq_model_invalidate_cache(casq_model* m) {
+  if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_model_invalidate_cache: NULL model");
+  m->tab_key.clear();
+  return CASQ_OK;
+}
+
 extern "C" int casq_model_get(const casq_model* m, double* frame_evals, double* frame_basis, double* dressed_evals,
                               double* dressed_states) {
   if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_model_get: NULL model");

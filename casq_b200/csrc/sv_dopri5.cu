@@ -1,0 +1,490 @@
+// casq_b200: adaptive Dormand-Prince 5(4) state-vector stepper for small Hilbert spaces (dim 2..4), one
+// trajectory per thread, per-thread step control.
+//
+// Replaces the "jax_odeint" method behind QiskitPulseBackend.solve (ODESolverMethod.QISKIT_DYNAMICS_JAX_ODEINT,
+// src/casq/backends/pulse_backend.py:65; the optimizer's documented method, docs/source/user_guide/
+// pulse_optimizer.rst:44 with {"atol":1e-6,"rtol":1e-8,"hmax":dt}).  The control flow follows the PUBLISHED
+// algorithm of jax.experimental.ode.odeint (jax 0.4.6, not in /root/reference):
+// Hairer initial step (order 4), FSAL, error ratio = RMS(err/(atol+rtol*max(|y0|,|y1|))), accept iff <= 1,
+// dt <- dt*min(10, max(0.9*ratio^-1/5, ratio<1 ? 1 : 0.2)) clipped to [0,hmax], steps run PAST each output
+// time and outputs come from the 4th-order interpolant of the last accepted step.
+//
+// Unlike the fixed-step kernel the time points differ per trajectory, so carrier and Bohr phases are
+// evaluated with fp64 sincos per stage (phases reach ~2e3 rad: fp32 is not an option).
+#include <cstring>
+
+#include "common.cuh"
+#include "envelope.cuh"
+
+#define DP_MAXD 4
+#define DP_MAXK 2
+#define DP_MAXE 6
+
+struct Dopri5Args {
+  long long B;
+  int T;                 // merged time points (t0 ... t1)
+  const double* tpts;    // [T] device
+  const char* keep;      // [T]
+  int T_out;             // number of kept points
+  const double* params;  // SoA
+  const double* y0;
+  int y0_batched;
+  double* out;        // [B][T_out][D] c128
+  long long* nsteps;  // [B][2] attempted, accepted (may be NULL)
+  int* status;        // [B] 0 ok, 1 mxstep hit, 2 dt underflow (may be NULL)
+  DevSlots slots;
+  int n_total;
+  double dt_sample;
+  double rtol, atol, hmax;
+  long long mxstep;
+  int rwa;
+  unsigned emask;  // which upper entries carry anything
+  int has_diag;
+  double two_pi_nu[DP_MAXK];
+  double bohr[DP_MAXE];
+  double Sr[DP_MAXE], Si[DP_MAXE];
+  double Pr[DP_MAXK][DP_MAXE], Pi[DP_MAXK][DP_MAXE];
+  double Nr[DP_MAXK][DP_MAXE], Ni[DP_MAXK][DP_MAXE];
+  double Sd[DP_MAXD];
+  double Pdr[DP_MAXK][DP_MAXD], Pdi[DP_MAXK][DP_MAXD];
+  int identityU;
+  double Ur[DP_MAXD][DP_MAXD], Ui[DP_MAXD][DP_MAXD];
+};
+
+// numpy float floor-division a // b (b > 0), then clip to [-1, n_total]
+__device__ __forceinline__ int dev_sample_index(double t, double dt, int n_total) {
+  double mod = fmod(t, dt);
+  double div = (t - mod) / dt;
+  if (mod != 0.0 && (mod < 0)) div -= 1.0;
+  double fl = 0.0;
+  if (div != 0.0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  }
+  if (fl < -1.0) fl = -1.0;
+  if (fl > (double)n_total) fl = (double)n_total;
+  return (int)fl;
+}
+
+template <int D, int KA>
+struct DpState {
+  int cur_idx;
+  dcplx env[KA];
+};
+
+template <int D, int KA>
+__device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, DpState<D, KA>& st, double t,
+                                       const double* yr, const double* yi, double* kr, double* ki) {
+  const int gidx = dev_sample_index(t, a.dt_sample, a.n_total);
+  if (gidx != st.cur_idx) {
+    st.cur_idx = gidx;
+    casq_channel_envelopes<KA>(a.slots, a.params, a.B, b, gidx, st.env);
+  }
+  double zr[KA], zi[KA];
+#pragma unroll
+  for (int k = 0; k < KA; k++) {
+    double s, c;
+    sincos(a.two_pi_nu[k] * t, &s, &c);
+    zr[k] = st.env[k].re * c - st.env[k].im * s;
+    zi[k] = st.env[k].re * s + st.env[k].im * c;
+  }
+  double wr[D], wi[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double h = 0.0;
+    if (a.has_diag) {
+      h = a.Sd[i];
+#pragma unroll
+      for (int k = 0; k < KA; k++) h += 2.0 * (zr[k] * a.Pdr[k][i] - zi[k] * a.Pdi[k][i]);
+    }
+    wr[i] = h * yr[i];
+    wi[i] = h * yi[i];
+  }
+  int e = 0;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+#pragma unroll
+    for (int j = i + 1; j < D; j++) {
+      if (a.emask & (1u << e)) {
+        double gr = a.Sr[e], gi = a.Si[e];
+#pragma unroll
+        for (int k = 0; k < KA; k++) {
+          // z*P + conj(z)*N
+          gr += zr[k] * (a.Pr[k][e] + a.Nr[k][e]) - zi[k] * (a.Pi[k][e] - a.Ni[k][e]);
+          gi += zr[k] * (a.Pi[k][e] + a.Ni[k][e]) + zi[k] * (a.Pr[k][e] - a.Nr[k][e]);
+        }
+        double s, c;
+        sincos(a.bohr[e] * t, &s, &c);
+        const double hr = gr * c - gi * s, hi = gr * s + gi * c;
+        wr[i] += hr * yr[j] - hi * yi[j];
+        wi[i] += hr * yi[j] + hi * yr[j];
+        wr[j] += hr * yr[i] + hi * yi[i];
+        wi[j] += hr * yi[i] - hi * yr[i];
+      }
+      e++;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    kr[i] = wi[i];
+    ki[i] = -wr[i];
+  }
+}
+
+__constant__ double DP_ALPHA[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+__constant__ double DP_BETA[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+__constant__ double DP_CERR[7] = {35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                                  -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60};
+__constant__ double DP_CMID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 51252292925.0 / 65400821598.0 / 2,
+                                  -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
+                                  -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
+
+template <int D, int KA>
+__global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  DpState<D, KA> st;
+  st.cur_idx = -2;
+#pragma unroll
+  for (int k = 0; k < KA; k++) st.env[k].re = st.env[k].im = 0.0;
+
+  double yr[D], yi[D];
+  {
+    const double* src = a.y0 + (a.y0_batched ? b * 2 * D : 0);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double sr = 0, si = 0;
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        const double ur = a.identityU ? (i == j ? 1.0 : 0.0) : a.Ur[j][i];
+        const double ui = a.identityU ? 0.0 : a.Ui[j][i];
+        sr += ur * src[2 * j] + ui * src[2 * j + 1];
+        si += ur * src[2 * j + 1] - ui * src[2 * j];
+      }
+      yr[i] = sr;
+      yi[i] = si;
+    }
+  }
+  double* outp = a.out + b * (long long)a.T_out * 2 * D;
+  int out_slot = 0;
+  auto emit = [&](const double* vr, const double* vi) {
+    double* o = outp + (long long)out_slot * 2 * D;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double sr = 0, si = 0;
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        const double ur = a.identityU ? (i == j ? 1.0 : 0.0) : a.Ur[i][j];
+        const double ui = a.identityU ? 0.0 : a.Ui[i][j];
+        sr += ur * vr[j] - ui * vi[j];
+        si += ur * vi[j] + ui * vr[j];
+      }
+      o[2 * i] = sr;
+      o[2 * i + 1] = si;
+    }
+    out_slot++;
+  };
+  if (a.keep[0]) emit(yr, yi);
+
+  double t = a.tpts[0];
+  // k[0] = f(y0, t0)
+  double kr[7][D], ki[7][D];
+  dp_rhs<D, KA>(a, b, st, t, yr, yi, kr[0], ki[0]);
+
+  // ---- initial step size (Hairer, Norsett, Wanner II.4; order 4)
+  double dt;
+  {
+    double d0 = 0, d1 = 0;
+    double sc[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      sc[i] = a.atol + hypot(yr[i], yi[i]) * a.rtol;
+      d0 += (yr[i] * yr[i] + yi[i] * yi[i]) / (sc[i] * sc[i]);
+      d1 += (kr[0][i] * kr[0][i] + ki[0][i] * ki[0][i]) / (sc[i] * sc[i]);
+    }
+    d0 = sqrt(d0);
+    d1 = sqrt(d1);
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    double tr[D], ti[D], fr[D], fi[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      tr[i] = yr[i] + h0 * kr[0][i];
+      ti[i] = yi[i] + h0 * ki[0][i];
+    }
+    dp_rhs<D, KA>(a, b, st, t + h0, tr, ti, fr, fi);
+    double d2 = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const double er = fr[i] - kr[0][i], ei = fi[i] - ki[0][i];
+      d2 += (er * er + ei * ei) / (sc[i] * sc[i]);
+    }
+    d2 = sqrt(d2) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / (d1 + d2), 1.0 / 5.0);
+    dt = fmin(100.0 * h0, h1);
+    dt = fmin(fmax(dt, 0.0), a.hmax);
+  }
+
+  long long n_att = 0, n_acc = 0;
+  int status = 0;
+  int next = 1;  // next merged time point to produce
+  long long i_target = 0;
+  while (next < a.T) {
+    const double target = a.tpts[next];
+    if (!(t < target)) {
+      // cannot happen before the first step (t0 < t1); guard against equal points
+      next++;
+      continue;
+    }
+    if (i_target >= a.mxstep) {
+      status = 1;
+      break;
+    }
+    if (!(dt > 0.0)) {
+      status = 2;
+      break;
+    }
+    // ---- one attempted step
+#pragma unroll
+    for (int s = 1; s < 7; s++) {
+      double tr[D], ti[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        double ar = 0, ai = 0;
+#pragma unroll
+        for (int q = 0; q < s; q++) {
+          ar += DP_BETA[s - 1][q] * kr[q][i];
+          ai += DP_BETA[s - 1][q] * ki[q][i];
+        }
+        tr[i] = yr[i] + dt * ar;
+        ti[i] = yi[i] + dt * ai;
+      }
+      dp_rhs<D, KA>(a, b, st, t + dt * DP_ALPHA[s - 1], tr, ti, kr[s], ki[s]);
+    }
+    double y1r[D], y1i[D];
+    double ratio = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double sr = 0, si = 0, er = 0, ei = 0;
+#pragma unroll
+      for (int q = 0; q < 7; q++) {
+        const double cs = (q < 6) ? DP_BETA[5][q] : 0.0;
+        sr += cs * kr[q][i];
+        si += cs * ki[q][i];
+        er += DP_CERR[q] * kr[q][i];
+        ei += DP_CERR[q] * ki[q][i];
+      }
+      y1r[i] = dt * sr + yr[i];
+      y1i[i] = dt * si + yi[i];
+      er *= dt;
+      ei *= dt;
+      const double tol = a.atol + a.rtol * fmax(hypot(yr[i], yi[i]), hypot(y1r[i], y1i[i]));
+      ratio += (er * er + ei * ei) / (tol * tol);
+    }
+    ratio = sqrt(ratio / D);
+    double new_dt;
+    if (ratio == 0.0) {
+      new_dt = dt * 10.0;
+    } else {
+      const double dfac = ratio < 1.0 ? 1.0 : 0.2;
+      new_dt = dt * fmin(10.0, fmax(pow(ratio, -1.0 / 5.0) * 0.9, dfac));
+    }
+    new_dt = fmin(fmax(new_dt, 0.0), a.hmax);
+    n_att++;
+    i_target++;
+    if (ratio <= 1.0) {
+      n_acc++;
+      const double t_new = t + dt;
+      // outputs inside (t, t_new]: 4th-order interpolant fitted to this step
+      if (t_new >= target) {
+        double pa_r[D], pa_i[D], pb_r[D], pb_i[D], pc_r[D], pc_i[D], pd_r[D], pd_i[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double mr = 0, mi = 0;
+#pragma unroll
+          for (int q = 0; q < 7; q++) {
+            mr += DP_CMID[q] * kr[q][i];
+            mi += DP_CMID[q] * ki[q][i];
+          }
+          const double ymr = yr[i] + dt * mr, ymi = yi[i] + dt * mi;
+          const double d0r = dt * kr[0][i], d0i = dt * ki[0][i], d1r = dt * kr[6][i], d1i = dt * ki[6][i];
+          pa_r[i] = -2.0 * d0r + 2.0 * d1r - 8.0 * yr[i] - 8.0 * y1r[i] + 16.0 * ymr;
+          pa_i[i] = -2.0 * d0i + 2.0 * d1i - 8.0 * yi[i] - 8.0 * y1i[i] + 16.0 * ymi;
+          pb_r[i] = 5.0 * d0r - 3.0 * d1r + 18.0 * yr[i] + 14.0 * y1r[i] - 32.0 * ymr;
+          pb_i[i] = 5.0 * d0i - 3.0 * d1i + 18.0 * yi[i] + 14.0 * y1i[i] - 32.0 * ymi;
+          pc_r[i] = -4.0 * d0r + d1r - 11.0 * yr[i] - 5.0 * y1r[i] + 16.0 * ymr;
+          pc_i[i] = -4.0 * d0i + d1i - 11.0 * yi[i] - 5.0 * y1i[i] + 16.0 * ymi;
+          pd_r[i] = d0r;
+          pd_i[i] = d0i;
+        }
+        while (next < a.T && a.tpts[next] <= t_new) {
+          const double rel = (a.tpts[next] - t) / (t_new - t);
+          if (a.keep[next]) {
+            double vr[D], vi[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+              vr[i] = (((pa_r[i] * rel + pb_r[i]) * rel + pc_r[i]) * rel + pd_r[i]) * rel + yr[i];
+              vi[i] = (((pa_i[i] * rel + pb_i[i]) * rel + pc_i[i]) * rel + pd_i[i]) * rel + yi[i];
+            }
+            emit(vr, vi);
+          }
+          next++;
+          i_target = 0;
+        }
+      }
+      t = t_new;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        yr[i] = y1r[i];
+        yi[i] = y1i[i];
+        kr[0][i] = kr[6][i];  // FSAL
+        ki[0][i] = ki[6][i];
+      }
+    }
+    dt = new_dt;
+  }
+  // failed trajectories: fill the remaining outputs with NaN so nobody mistakes them for results
+  if (status != 0) {
+    double nanv[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) nanv[i] = nan("");
+    for (; next < a.T; next++)
+      if (a.keep[next]) emit(nanv, nanv);
+  }
+  if (a.nsteps) {
+    a.nsteps[2 * b] = n_att;
+    a.nsteps[2 * b + 1] = n_acc;
+  }
+  if (a.status) a.status[b] = status;
+}
+
+int casq_prepare_slots(const casq_model* m, int n_slots, const casq_pulse_slot* slots, DevSlots* ds, int* active,
+                       int* n_active, int* n_total);
+
+extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
+                                    const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1,
+                                    double rtol, double atol, double hmax, int64_t mxstep, int T, const double* t_eval,
+                                    double* out_dev, int64_t* nsteps_dev, int32_t* status_dev, void* stream) {
+  if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: NULL model");
+  if (B < 0 || !y0_dev || !out_dev || (n_slots > 0 && !params_dev)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: NULL buffer");
+  if (!(t1 > t0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: need t1 > t0");
+  if (!(rtol > 0) || !(atol > 0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: rtol and atol must be > 0");
+  DevSlots ds;
+  int active[CASQ_MAX_SLOTS], KA = 0, n_total = 0;
+  int rc = casq_prepare_slots(m, n_slots, slots, &ds, active, &KA, &n_total);
+  if (rc != CASQ_OK) return rc;
+  if (B == 0) return CASQ_OK;
+  if (KA == 0) {
+    if (m->K < 1) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "model without channels");
+    active[0] = 0;
+    KA = 1;
+  }
+  const int d = m->d;
+  if (d < 2 || d > DP_MAXD || KA > DP_MAXK)
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: dim %d with %d active channels has no kernel yet", d, KA);
+  cudaStream_t st = (cudaStream_t)stream;
+  CASQ_CUDA(cudaSetDevice(m->device));
+
+  // merged output grid (same trimming rule as the fixed-step path)
+  std::vector<double> pts;
+  std::vector<char> keep;
+  if (!t_eval) {
+    if (T != 2) CASQ_FAIL(CASQ_ERR_INVALID, "t_eval is NULL: T must be 2 (t0 and t1), got %d", T);
+    pts = {t0, t1};
+    keep = {1, 1};
+  } else {
+    if (T < 1) CASQ_FAIL(CASQ_ERR_INVALID, "t_eval needs at least one point");
+    for (int i = 1; i < T; i++)
+      if (!(t_eval[i] > t_eval[i - 1])) CASQ_FAIL(CASQ_ERR_INVALID, "t_eval must be strictly increasing");
+    if (t_eval[0] < t0 || t_eval[T - 1] > t1) CASQ_FAIL(CASQ_ERR_INVALID, "t_eval must lie inside [t0, t1]");
+    if (t_eval[0] != t0) {
+      pts.push_back(t0);
+      keep.push_back(0);
+    }
+    for (int i = 0; i < T; i++) {
+      pts.push_back(t_eval[i]);
+      keep.push_back(1);
+    }
+    if (t_eval[T - 1] != t1) {
+      pts.push_back(t1);
+      keep.push_back(0);
+    }
+  }
+  const int TM = (int)pts.size();
+  if ((rc = m->tab_times.ensure(TM * sizeof(double)))) return rc;
+  if ((rc = m->consts.ensure(TM))) return rc;
+  m->tab_key.clear();  // the fixed-step table cache shares these buffers
+  CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, pts.data(), TM * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->consts.p, keep.data(), TM, cudaMemcpyHostToDevice, st));
+
+  Dopri5Args a;
+  memset(&a, 0, sizeof(a));
+  a.B = B;
+  a.T = TM;
+  a.tpts = (const double*)m->tab_times.p;
+  a.keep = (const char*)m->consts.p;
+  a.T_out = T;
+  a.params = params_dev;
+  a.y0 = y0_dev;
+  a.y0_batched = y0_batched;
+  a.out = out_dev;
+  a.nsteps = (long long*)nsteps_dev;
+  a.status = status_dev;
+  a.slots = ds;
+  a.n_total = n_total;
+  a.dt_sample = m->dt;
+  a.rtol = rtol;
+  a.atol = atol;
+  a.hmax = (hmax > 0) ? hmax : INFINITY;
+  a.mxstep = (mxstep > 0) ? mxstep : (1LL << 62);
+  a.rwa = m->rwa;
+  for (int k = 0; k < KA; k++) a.two_pi_nu[k] = 2.0 * M_PI * m->nu[active[k]];
+  int e = 0;
+  for (int i = 0; i < d; i++) {
+    a.Sd[i] = m->S[i * d + i].real();
+    if (a.Sd[i] != 0.0) a.has_diag = 1;
+    for (int k = 0; k < KA; k++) {
+      cplx p = m->P[((size_t)active[k] * d + i) * d + i];
+      a.Pdr[k][i] = p.real();
+      a.Pdi[k][i] = p.imag();
+      if (std::abs(p) != 0.0) a.has_diag = 1;
+    }
+    for (int j = 0; j < d; j++) {
+      a.Ur[i][j] = m->U[i * d + j].real();
+      a.Ui[i][j] = m->U[i * d + j].imag();
+    }
+    for (int j = i + 1; j < d; j++) {
+      a.bohr[e] = m->fe[i] - m->fe[j];
+      cplx s = m->S[i * d + j];
+      a.Sr[e] = s.real();
+      a.Si[e] = s.imag();
+      bool any = std::abs(s) != 0.0;
+      for (int k = 0; k < KA; k++) {
+        cplx p = m->P[((size_t)active[k] * d + i) * d + j], n = m->N[((size_t)active[k] * d + i) * d + j];
+        a.Pr[k][e] = p.real();
+        a.Pi[k][e] = p.imag();
+        a.Nr[k][e] = n.real();
+        a.Ni[k][e] = n.imag();
+        any = any || std::abs(p) != 0.0 || std::abs(n) != 0.0;
+      }
+      if (any) a.emask |= (1u << e);
+      e++;
+    }
+  }
+  a.identityU = m->U_is_identity ? 1 : 0;
+  const int block = 64;
+  const unsigned grid = (unsigned)((B + block - 1) / block);
+#define LAUNCH(D_, K_)                                        \
+  if (d == D_ && KA == K_) {                                  \
+    sv_dopri5_kernel<D_, K_><<<grid, block, 0, st>>>(a);      \
+  }
+  LAUNCH(2, 1) LAUNCH(2, 2) LAUNCH(3, 1) LAUNCH(3, 2) LAUNCH(4, 1) LAUNCH(4, 2)
+#undef LAUNCH
+  CASQ_CUDA(cudaGetLastError());
+  return CASQ_OK;
+}

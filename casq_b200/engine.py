@@ -115,6 +115,76 @@ def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_
     return out
 
 
+def _prep_solve(model, slots, params, y0, t_eval, what):
+    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
+    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
+        raise CasqError(f"{what}: params must be a CUDA float64 tensor [n_slots, 5, B]")
+    params = params.contiguous()
+    slots = list(slots)
+    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
+        raise CasqError(f"{what}: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
+    B, d = params.shape[2], model.dim
+    y0_t = torch.as_tensor(np.asarray(y0) if not isinstance(y0, torch.Tensor) else y0).to(torch.complex128)
+    if y0_t.shape not in ((d,), (B, d)):
+        raise CasqError(f"{what}: y0 must be [{d}] or [{B},{d}], got {tuple(y0_t.shape)}")
+    y0_t = y0_t.to(dev).contiguous()
+    if t_eval is None:
+        T, te = 2, None
+    else:
+        te = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+        T = len(te)
+    return dev, params, slots, B, d, y0_t, T, te
+
+
+def solve_sv_dopri5(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_span, rtol: float = 1.4e-8,
+                    atol: float = 1.4e-8, hmax: float = 0.0, mxstep: int = 0, t_eval=None, return_stats: bool = False):
+    """Adaptive Dopri5 (jax.experimental.ode.odeint controller) for a batch of pulse points.
+
+    Returns CUDA complex128 [B, T, d]; with return_stats also (nsteps int64 [B,2], status int32 [B])."""
+    dev, params, slots, B, d, y0_t, T, te = _prep_solve(model, slots, params, y0, t_eval, "solve_sv_dopri5")
+    out = torch.empty((B, T, d), dtype=torch.complex128, device=dev)
+    nsteps = torch.zeros((B, 2), dtype=torch.int64, device=dev)
+    status = torch.zeros((B,), dtype=torch.int32, device=dev)
+    hmax = 0.0 if hmax is None or not np.isfinite(hmax) else float(hmax)
+    mxstep = 0 if mxstep is None or not np.isfinite(mxstep) else int(mxstep)
+    with torch.cuda.device(dev):
+        _native.check(
+            _native.load().casq_solve_sv_dopri5(
+                model.handle, len(slots), _native.make_slots(slots), B, params.data_ptr(), y0_t.data_ptr(),
+                1 if y0_t.dim() == 2 else 0, float(t_span[0]), float(t_span[1]), float(rtol), float(atol), hmax, mxstep,
+                T, te.ctypes.data if te is not None else None, out.data_ptr(), nsteps.data_ptr(), status.data_ptr(),
+                _stream_ptr(dev)),
+            "casq_solve_sv_dopri5",
+        )
+    return (out, nsteps, status) if return_stats else out
+
+
+def postprocess_sv(model: _native.NativeModel, times, raw: torch.Tensor, normalize: bool = True,
+                   want_states: bool = True, want_probs: bool = True):
+    """raw [B,T,d] (as returned by the solves) -> (states [B,T,d] lab/dressed/normalised, probs [B,T,d],
+    pops [B,T,2] = casq's {"0","1"} with every level >= 1 folded into "1")."""
+    if not (raw.is_cuda and raw.dtype == torch.complex128 and raw.dim() == 3 and raw.shape[2] == model.dim):
+        raise CasqError("postprocess_sv: raw must be a CUDA complex128 tensor [B, T, d]")
+    raw = raw.contiguous()
+    B, T, d = raw.shape
+    times = np.ascontiguousarray(np.asarray(times, dtype=np.float64))
+    if times.shape != (T,):
+        raise CasqError(f"postprocess_sv: need {T} times, got {times.shape}")
+    dev = raw.device
+    states = torch.empty_like(raw) if want_states else None
+    probs = torch.empty((B, T, d), dtype=torch.float64, device=dev) if want_probs else None
+    pops = torch.empty((B, T, 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(
+            _native.load().casq_postprocess_sv(
+                model.handle, B, T, times.ctypes.data, raw.data_ptr(), 1 if normalize else 0,
+                states.data_ptr() if states is not None else None, probs.data_ptr() if probs is not None else None,
+                pops.data_ptr(), _stream_ptr(dev)),
+            "casq_postprocess_sv",
+        )
+    return states, probs, pops
+
+
 def fp64_fma_probe(device=0, iters: int = 4096, reps: int = 5) -> float:
     """Measured fp64 FMA throughput (TFLOP/s) of this GPU: the roofline denominator for the RK4 kernel."""
     dev = _require_cuda(device)

@@ -1,0 +1,28 @@
+"""Drag pulse gate (drop-in for src/casq/gates/drag_pulse_gate.py)."""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy.typing as npt
+
+from ..pulse import Drag, ScalableSymbolicPulse
+from .pulse_gate import PulseGate
+
+
+class DragPulseGate(PulseGate):
+    """DragPulseGate: forwards to the ``Drag`` envelope family; optimisable parameters ['sigma', 'beta'].
+
+    Args: duration (samples), amplitude, angle (default None), limit_amplitude, name.
+    """
+
+    def __init__(self, duration: int, amplitude: float, angle: Optional[float] = None,
+                 limit_amplitude: bool = True, name: Optional[str] = None) -> None:
+        super().__init__(1, duration, amplitude, angle, limit_amplitude, name)
+
+    def pulse(self, parameters: Optional[dict[str, Any]] = None) -> ScalableSymbolicPulse:
+        return Drag(duration=self.duration, amp=self.amplitude, angle=self.angle,
+                     limit_amplitude=self.limit_amplitude, name=self.name, **(parameters or {}))
+
+    def to_parameters_dict(self, parameters: npt.NDArray) -> dict[str, Any]:
+        """Array in order ['sigma', 'beta'] -> dictionary."""
+        return {"sigma": parameters[0], "beta": parameters[1]}

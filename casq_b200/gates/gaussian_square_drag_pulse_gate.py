@@ -1,0 +1,28 @@
+"""Gaussian square drag pulse gate (drop-in for src/casq/gates/gaussian_square_drag_pulse_gate.py)."""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy.typing as npt
+
+from ..pulse import GaussianSquareDrag, ScalableSymbolicPulse
+from .pulse_gate import PulseGate
+
+
+class GaussianSquareDragPulseGate(PulseGate):
+    """GaussianSquareDragPulseGate: forwards to the ``GaussianSquareDrag`` envelope family; optimisable parameters ['sigma', 'width', 'beta'].
+
+    Args: duration (samples), amplitude, angle (default 0), limit_amplitude, name.
+    """
+
+    def __init__(self, duration: int, amplitude: float, angle: Optional[float] = 0,
+                 limit_amplitude: bool = True, name: Optional[str] = None) -> None:
+        super().__init__(1, duration, amplitude, angle, limit_amplitude, name)
+
+    def pulse(self, parameters: Optional[dict[str, Any]] = None) -> ScalableSymbolicPulse:
+        return GaussianSquareDrag(duration=self.duration, amp=self.amplitude, angle=self.angle,
+                     limit_amplitude=self.limit_amplitude, name=self.name, **(parameters or {}))
+
+    def to_parameters_dict(self, parameters: npt.NDArray) -> dict[str, Any]:
+        """Array in order ['sigma', 'width', 'beta'] -> dictionary."""
+        return {"sigma": parameters[0], "width": parameters[1], "beta": parameters[2]}

@@ -90,6 +90,9 @@ int casq_model_set_dissipators(casq_model* m, int n, const double* ops);
 int casq_model_get(const casq_model* m, double* frame_evals, double* frame_basis, double* dressed_evals,
                    double* dressed_states);
 int casq_model_dim(const casq_model* m);
+/* Drop the cached stage table (carrier / Bohr-phase table of the last fixed-step time grid) so that the next
+ * solve rebuilds it; benchmarks call this every step so no precomputation is amortised outside the timing. */
+int casq_model_invalidate_cache(casq_model* m);
 
 /* ---- envelope sampler -------------------------------------------------------------------------
  * Replaces the per-solve InstructionToSignals.get_signals sampling (same code casq calls at
@@ -108,6 +111,26 @@ int casq_envelope_sample(int kind, int duration, int64_t B, const double* params
 int casq_solve_sv_rk4(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
                       const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1,
                       double max_dt, int T, const double* t_eval, double* out_dev, void* stream);
+
+/* casq_solve_sv_dopri5: ODESolverMethod.QISKIT_DYNAMICS_JAX_ODEINT (pulse_backend.py:65): adaptive
+ * Dormand-Prince 5(4) with jax.experimental.ode.odeint's controller (Hairer initial step, FSAL, RMS error
+ * ratio, factor clip [0.2, 10], safety 0.9, dense output by 4th-order interpolant).  hmax <= 0 -> inf,
+ * mxstep <= 0 -> unbounded (per output interval, like jax).  Optional per-point outputs:
+ *   nsteps_dev [B*2] int64 (attempted, accepted), status_dev [B] int32 (0 ok, 1 mxstep hit, 2 step underflow;
+ *   the remaining outputs of a failed point are NaN). */
+int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
+                         const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1,
+                         double rtol, double atol, double hmax, int64_t mxstep, int T, const double* t_eval,
+                         double* out_dev, int64_t* nsteps_dev, int32_t* status_dev, void* stream);
+
+/* ---- result post-processing ---------------------------------------------------------------------
+ * Replaces the per-time-point loop of get_experiment_result (src/casq/backends/qiskit/helpers.py:98-135)
+ * for state vectors: raw_dev [B*T*dim] c128 as returned by the solves above, times host [T].
+ *   states_dev [B*T*dim] c128  lab frame, dressed basis, normalised when `normalize`   (may be NULL)
+ *   probs_dev  [B*T*dim] f64   level probabilities                                      (may be NULL)
+ *   pops_dev   [B*T*2]   f64   casq populations {"0": level 0, "1": every other level}  (may be NULL) */
+int casq_postprocess_sv(casq_model* m, int64_t B, int T, const double* times, const double* raw_dev,
+                        int normalize, double* states_dev, double* probs_dev, double* pops_dev, void* stream);
 
 /* ---- measurement support ----------------------------------------------------------------------
  * casq_fp64_fma_probe: a pure DFMA kernel used by bench.py to MEASURE the fp64 roofline denominator

@@ -1,0 +1,311 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs (bit-level agreement is not expected for fp64 transcendental code; the bar is north_star's 1e-6 on
+state vectors -- these tests hold the kernels to 1e-9 or better where both sides run the same scheme)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from casq_b200 import engine
+from casq_b200._native import NativeModel
+from casq_b200.backends import BackendLibrary, PulseBackend, build
+from casq_b200.common.exceptions import CasqError
+from casq_b200.gates import DragPulseGate, GaussianPulseGate, GaussianSquarePulseGate, PulseCircuit
+from casq_b200.models import ControlModel, TransmonModel
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DT = O.MANILA_DT
+TOL_STATE = 1e-9  # same RK4 scheme on both sides; north_star's bar is 1e-6
+
+
+def _models(subsystems=(0,), frame="full", rwa=None, h_dict=None, carriers=None):
+    h_dict = O.MANILA if h_dict is None else h_dict
+    carriers = O.MANILA_CARRIERS if carriers is None else carriers
+    st, ops, ch, _ = O.parse_hamiltonian_dict(h_dict, list(subsystems) if subsystems is not None else None)
+    rf = {"full": st, "diag": np.diag(st).real, "none": None, "shifted": np.diag(st).real + 2e8}[frame]
+    om = O.OracleModel(st, ops, ch, carriers, DT, rotating_frame=rf, rwa_cutoff_freq=rwa)
+    nm = NativeModel(st, ops, [carriers[c] for c in ch], DT, rotating_frame=rf, rwa_cutoff_freq=rwa)
+    return om, nm, ch
+
+
+def _rand_params(rng, kind, B, duration):
+    p = dict(amp=rng.uniform(0.05, 0.9, B), angle=rng.uniform(-np.pi, np.pi, B))
+    if kind != "constant":
+        p["sigma"] = rng.uniform(duration / 10, duration / 2, B)
+    if "square" in kind:
+        p["width"] = rng.uniform(0, duration * 0.7, B)
+    if "drag" in kind:
+        p["beta"] = rng.uniform(-3, 3, B)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["constant", "gaussian", "drag", "gaussian_square", "gaussian_square_drag"])
+def test_envelope_sampler_matches_oracle(kind):
+    rng = np.random.default_rng(11)
+    B, dur = 257, 48
+    p = _rand_params(rng, kind, B, dur)
+    want = O.envelope_samples(kind, dur, **p)
+    got = engine.envelope_sample(kind, dur, engine.pack_params([p], device="cuda")[0]).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-14
+
+
+def test_envelope_sampler_golden_and_edge_cases():
+    g = np.load(os.path.join(G, "envelopes.npz"))
+    for kind, keys in [("constant", ()), ("gaussian", ("sigma",)), ("drag", ("sigma", "beta")),
+                       ("gaussian_square", ("sigma", "width")), ("gaussian_square_drag", ("sigma", "width", "beta"))]:
+        p = dict(amp=g["p_amp"], angle=g["p_angle"], **{k: g[f"p_{k}"] for k in keys})
+        got = engine.envelope_sample(kind, int(g["duration"]), engine.pack_params([p], device="cuda")[0]).cpu().numpy()
+        assert np.abs(got - g[kind]).max() < 1e-14
+    # width = 0 and width = duration, duration = 1, empty batch
+    for w in (0.0, 16.0):
+        p = dict(amp=0.5, angle=0.0, sigma=3.0, width=w)
+        got = engine.envelope_sample("gaussian_square", 16, engine.pack_params([p], device="cuda")[0]).cpu().numpy()
+        assert np.abs(got - O.envelope_samples("gaussian_square", 16, **p)).max() < 1e-15
+    one = engine.envelope_sample("gaussian", 1, engine.pack_params([dict(amp=0.3, sigma=2.0)], device="cuda")[0])
+    assert np.abs(one.cpu().numpy() - O.envelope_samples("gaussian", 1, amp=0.3, sigma=2.0)).max() < 1e-15
+    empty = engine.envelope_sample("gaussian", 4, torch.zeros((5, 0), dtype=torch.float64, device="cuda"))
+    assert empty.shape == (0, 4)
+
+
+@pytest.mark.parametrize("kind", ["constant", "gaussian", "drag", "gaussian_square", "gaussian_square_drag"])
+@pytest.mark.parametrize("frame,rwa", [("full", None), ("none", None), ("shifted", None), ("full", 3.0e9), ("shifted", 3.0e9)])
+def test_rk4_d3_matches_oracle(kind, frame, rwa):
+    rng = np.random.default_rng(5)
+    om, nm, ch = _models((0,), frame, rwa)
+    B, dur = 33, 40
+    p = _rand_params(rng, kind, B, dur)
+    samples = O.channel_samples(ch, [O.PulseSpec(kind, "d0", dur)], [p])
+    span = (0.0, dur * DT)
+    te = np.linspace(0, dur * DT, 6)
+    sub = 40 if frame != "none" else 160
+    _, want = O.rk4_solve(om, samples, np.array([1, 0, 0]), span, DT / sub, te)
+    got = engine.solve_sv_rk4(nm, [(kind, ch.index("d0"), 0, dur)], engine.pack_params([p], device="cuda"),
+                              np.array([1, 0, 0]), span, DT / sub, te).cpu().numpy()
+    assert got.shape == (B, 6, 3)
+    assert np.abs(got - want).max() < TOL_STATE
+
+
+def test_rk4_golden_fixture_and_postprocess():
+    g = np.load(os.path.join(G, "rk4_drag_d3.npz"))
+    om, nm, ch = _models((0,), "full")
+    p = dict(amp=g["amp"], angle=0.0, sigma=float(g["sigma"]), beta=g["beta"])
+    raw = engine.solve_sv_rk4(nm, [("drag", 0, 0, int(g["duration"]))], engine.pack_params([p], device="cuda"),
+                              np.array([1, 0, 0]), (0.0, int(g["t_final"]) * DT), DT / 40, g["t_eval"])
+    assert np.abs(raw.cpu().numpy() - g["raw"]).max() < TOL_STATE
+    states, probs, pops = engine.postprocess_sv(nm, g["t_eval"], raw)
+    assert np.abs(states.cpu().numpy() - g["states"]).max() < TOL_STATE
+    pr = np.abs(g["states"]) ** 2
+    assert np.abs(probs.cpu().numpy() - pr).max() < TOL_STATE
+    assert np.abs(pops.cpu().numpy()[..., 0] - pr[..., 0]).max() < TOL_STATE
+    assert np.abs(pops.cpu().numpy()[..., 1] - pr[..., 1:].sum(-1)).max() < TOL_STATE
+
+
+def test_rk4_two_level_and_four_level_systems():
+    rng = np.random.default_rng(9)
+    for dims, d in (({"0": 2}, 2), ({"0": 2, "1": 2}, 4), ({"0": 4}, 4)):
+        terms = ["_SUM[i,0,{n},wq{{i}}/2*(I{{i}}-Z{{i}})]".format(n=len(dims) - 1), "_SUM[i,0,{n},om{{i}}*X{{i}}||D{{i}}]".format(n=len(dims) - 1)]
+        variables = {"wq0": 2 * np.pi * 4.9e9, "om0": 6e8, "wq1": 2 * np.pi * 5.1e9, "om1": 5e8, "j": 4e7, "al": -2e9}
+        if len(dims) == 2:
+            terms += ["j*Sp0*Sm1", "j*Sm0*Sp1", "om0*Y1||U0"]
+        if d == 4 and len(dims) == 1:
+            terms += ["al/2*O0*O0", "-al/2*O0"]
+        hd = {"h_str": terms, "qub": dims, "vars": variables}
+        carriers = {"d0": 4.9e9, "d1": 5.1e9, "u0": 5.1e9}
+        for frame in ("full", "diag"):
+            om, nm, ch = _models(None, frame, None, hd, carriers)
+            assert om.dim == d
+            B, dur = 19, 24
+            specs = [O.PulseSpec("drag", "d0", dur)]
+            slots = [("drag", ch.index("d0"), 0, dur)]
+            ps = [_rand_params(rng, "drag", B, dur)]
+            if "u0" in ch:  # second active channel, overlapping in time
+                specs.append(O.PulseSpec("gaussian_square", "u0", 16, start=4))
+                slots.append(("gaussian_square", ch.index("u0"), 4, 16))
+                ps.append(_rand_params(rng, "gaussian_square", B, 16))
+            samples = O.channel_samples(ch, specs, ps)
+            y0 = rng.normal(size=(B, d)) + 1j * rng.normal(size=(B, d))
+            y0 /= np.linalg.norm(y0, axis=1, keepdims=True)
+            span = (0.0, dur * DT)
+            _, want = O.rk4_solve(om, samples, y0, span, DT / 50)
+            got = engine.solve_sv_rk4(nm, slots, engine.pack_params(ps, device="cuda"), y0, span, DT / 50).cpu().numpy()
+            assert np.abs(got - want).max() < TOL_STATE, (dims, frame)
+
+
+def test_rk4_multi_slot_same_channel_and_ragged_grid():
+    """Two pulses on one channel (second starts later), max_dt that does not divide dt, t_eval off the grid."""
+    rng = np.random.default_rng(21)
+    om, nm, ch = _models((0,), "full")
+    B = 8
+    specs = [O.PulseSpec("gaussian", "d0", 16, start=0), O.PulseSpec("drag", "d0", 20, start=20)]
+    ps = [_rand_params(rng, "gaussian", B, 16), _rand_params(rng, "drag", B, 20)]
+    samples = O.channel_samples(ch, specs, ps)
+    span = (0.0, 40 * DT)
+    te = np.array([0.31, 7.77, 20.0, 33.3]) * DT
+    _, want = O.rk4_solve(om, samples, np.array([0, 1, 0]), span, DT / 37.3, te)
+    got = engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16), ("drag", 0, 20, 20)], engine.pack_params(ps, device="cuda"),
+                              np.array([0, 1, 0]), span, DT / 37.3, te).cpu().numpy()
+    assert got.shape == (B, 4, 3) and np.abs(got - want).max() < TOL_STATE
+
+
+def test_rk4_full_size_properties():
+    """BASELINE cfg 2 at full size (1e5 points, S = 10280): size-independent checks."""
+    om, nm, ch = _models((0,), "full")
+    beta, amp = np.linspace(-5, 5, 250), np.linspace(0.02, 0.5, 400)
+    bb, aa = np.meshgrid(beta, amp, indexing="ij")
+    p = dict(amp=aa.ravel(), angle=0.0, sigma=64.0, beta=bb.ravel())
+    params = engine.pack_params([p], device="cuda")
+    span = (0.0, 257 * DT)
+    slots = [("drag", 0, 0, 256)]
+    y = engine.solve_sv_rk4(nm, slots, params, np.array([1, 0, 0]), span, DT / 40)
+    assert y.shape == (100000, 2, 3)
+    yf = y[:, 1]
+    norms = torch.linalg.vector_norm(yf, dim=1)
+    assert float((norms - 1).abs().max()) < 1e-5  # RK4 is not exactly unitary; drift is O(S h^5)
+    # linearity in the initial state: solve(a|0> + b|1>) = a solve(|0>) + b solve(|1>)
+    sel = torch.arange(0, 100000, 997, device="cuda")
+    sub = params[:, :, sel].contiguous()
+    y1 = engine.solve_sv_rk4(nm, slots, sub, np.array([0, 1, 0]), span, DT / 40)[:, 1]
+    a, b = 0.6, 0.8j
+    ymix = engine.solve_sv_rk4(nm, slots, sub, np.array([a, b, 0]), span, DT / 40)[:, 1]
+    assert float((ymix - (a * yf[sel] + b * y1)).abs().max()) < 1e-12
+    # beta -> -beta with a real envelope conjugates nothing physical: P1 is symmetric only approximately,
+    # but the amp = 0.02..0.5 sweep must contain a pi-pulse (P1 > 0.99) near amp ~ 0.111 at beta = 0
+    p1 = (yf[:, 1].abs() ** 2).reshape(250, 400)
+    row = p1[125, :150]  # beta ~ 0.02, amp < 0.2 (the 3 pi pulse near amp 0.33 also inverts)
+    k = int(row.argmax())
+    assert float(row[k]) > 0.99 and 0.10 < amp[k] < 0.12
+    # oracle spot check at full S on 3 points
+    idx = np.array([0, 50321, 99999])
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", 256)], [dict(amp=p["amp"][idx], angle=0.0, sigma=64.0, beta=p["beta"][idx])])
+    _, want = O.rk4_solve(om, samples, np.array([1, 0, 0]), span, DT / 40)
+    assert np.abs(y.cpu().numpy()[idx] - want).max() < TOL_STATE
+
+
+def test_dopri5_matches_oracle_and_golden():
+    g = np.load(os.path.join(G, "dopri5_drag_d3.npz"))
+    om, nm, ch = _models((0,), "full")
+    p = dict(amp=float(g["amp"]), angle=0.0, sigma=g["sigma"], beta=g["beta"])
+    out, nsteps, status = engine.solve_sv_dopri5(nm, [("drag", 0, 0, int(g["duration"]))], engine.pack_params([p], device="cuda"),
+                                                 np.array([1, 0, 0]), (0.0, int(g["duration"]) * DT), rtol=1e-8, atol=1e-6,
+                                                 hmax=DT, return_stats=True)
+    assert int(status.abs().sum()) == 0
+    # same controller => same accept/reject sequence; allow a couple of borderline decisions to differ
+    assert np.abs(nsteps.cpu().numpy() - g["steps"]).max() <= 0.02 * g["steps"].max()
+    assert np.abs(out.cpu().numpy() - g["raw"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("frame,rwa", [("full", None), ("shifted", None), ("full", 3.0e9)])
+def test_dopri5_dense_output_and_frames(frame, rwa):
+    rng = np.random.default_rng(3)
+    om, nm, ch = _models((0,), frame, rwa)
+    B, dur = 6, 24
+    p = _rand_params(rng, "drag", B, dur)
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p])
+    span = (0.0, dur * DT)
+    te = np.linspace(0, dur * DT, 7)
+    _, want, steps = O.dopri5_jax_solve(om, samples, np.array([1, 0, 0]), span, te, rtol=1e-9, atol=1e-9)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("drag", 0, 0, dur)], engine.pack_params([p], device="cuda"),
+                                             np.array([1, 0, 0]), span, rtol=1e-9, atol=1e-9, t_eval=te, return_stats=True)
+    assert int(status.abs().sum()) == 0 and got.shape == (B, 7, 3)
+    # Sampled envelopes make the controller reject ~40% of its steps at sample boundaries, and which side of a
+    # boundary a stage lands on is decided at the 1e-16 level: CUDA and numpy follow step sequences that differ
+    # in a handful of decisions (test_dopri5_smooth_case_is_step_exact shows the controller itself is exact).
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-6  # north_star's state-vector bar
+    assert np.abs(ns.cpu().numpy() - steps).max() <= 0.02 * steps.max()
+
+
+def test_dopri5_smooth_case_is_step_exact():
+    """Constant envelope over a window longer than the span: no discontinuity, so the CUDA controller must take
+    exactly the oracle's accept/reject sequence and agree to rounding."""
+    om, nm, ch = _models((0,), "full")
+    p = dict(amp=np.array([0.6, 0.2, 0.9]), angle=np.array([0.3, -1.0, 2.0]))
+    samples = O.channel_samples(ch, [O.PulseSpec("constant", "d0", 40)], [p])
+    span = (0.0, 24 * DT)
+    te = np.linspace(0, 24 * DT, 5)
+    for tol in (1e-6, 1e-8, 1e-10):
+        _, want, steps = O.dopri5_jax_solve(om, samples, np.array([1, 0, 0]), span, te, rtol=tol, atol=tol)
+        got, ns, status = engine.solve_sv_dopri5(nm, [("constant", 0, 0, 40)], engine.pack_params([p], device="cuda"),
+                                                 np.array([1, 0, 0]), span, rtol=tol, atol=tol, t_eval=te, return_stats=True)
+        assert np.array_equal(ns.cpu().numpy(), steps) and int(status.abs().sum()) == 0
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-12
+
+
+def test_dopri5_mxstep_reports_failure():
+    om, nm, ch = _models((0,), "full")
+    p = dict(amp=0.5, angle=0.0, sigma=8.0, beta=1.0)
+    out, ns, status = engine.solve_sv_dopri5(nm, [("drag", 0, 0, 32)], engine.pack_params([p], device="cuda"),
+                                             np.array([1, 0, 0]), (0.0, 32 * DT), rtol=1e-10, atol=1e-10, mxstep=5,
+                                             return_stats=True)
+    assert int(status[0]) == 1 and bool(torch.isnan(out[0, -1].real).all())
+
+
+def test_backend_solve_matches_oracle_flow():
+    """The drop-in call: same circuit API as casq, results vs the oracle's restatement of casq's flow."""
+    h = TransmonModel.manila(extracted_qubits=[0])
+    c = ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+    backend = build(BackendLibrary.B200, h, c, seed=42)
+    om, _, ch = _models((0,), "full")
+    gate = DragPulseGate(duration=48, amplitude=0.7)
+    circuit = PulseCircuit.from_pulse_gate(gate, {"sigma": 12.0, "beta": 1.5})
+    spec, par = [O.PulseSpec("drag", "d0", 48)], [dict(amp=0.7, angle=0.0, sigma=12.0, beta=1.5)]
+    M = PulseBackend.ODESolverMethod
+    sol = backend.solve(circuit, M.QISKIT_DYNAMICS_RK4, steps=9, run_options={"max_dt": DT / 40})
+    ref = O.casq_solve(om, spec, par, method="RK4", steps=9, run_options={"max_dt": DT / 40})
+    assert isinstance(sol, PulseBackend.Solution) and len(sol.states) == 9 and len(sol.counts) == 9
+    np.testing.assert_allclose(sol.times, ref["times"], rtol=0, atol=0)
+    got = np.array([s.data for s in sol.states])
+    assert np.abs(got - ref["states"][0]).max() < TOL_STATE
+    for a, b in zip(sol.populations, ref["populations"]):
+        assert set(a) <= {"0", "1"} and all(abs(a.get(k, 0.0) - b.get(k, 0.0)) < 1e-9 for k in ("0", "1"))
+    assert all(sum(cn.values()) == 1024 for cn in sol.counts) and sol.counts[0] == {"0": 1024}
+    assert sol.shots == 1024 and len(sol.iq_data[-1]) == 1024 and len(sol.samples[-1]) == 1024
+    # adaptive, default (jax) tolerances and the scipy-named method: close to the tight-tolerance truth
+    truth = O.casq_solve(om, spec, par, method="DOP853", run_options={"rtol": 1e-12, "atol": 1e-12})["states"][0, -1]
+    for m in (M.QISKIT_DYNAMICS_JAX_ODEINT, M.SCIPY_DOP853):
+        s2 = backend.solve(circuit, m)
+        assert len(s2.states) == 2 and np.abs(s2.states[-1].data - truth).max() < 1e-4  # solver accuracy at 1.4e-8
+    # seeded sampling is reproducible; enum wins over run_options["method"]
+    s3 = backend.solve(circuit, M.QISKIT_DYNAMICS_RK4, run_options={"max_dt": DT / 40, "method": "DOP853"})
+    s4 = backend.solve(circuit, M.QISKIT_DYNAMICS_RK4, run_options={"max_dt": DT / 40})
+    assert s3.counts == s4.counts and s3.samples == s4.samples
+    with pytest.raises(CasqError, match="max_dt"):
+        backend.solve(circuit, M.QISKIT_DYNAMICS_RK4)
+    with pytest.raises(CasqError, match="LSODA"):
+        backend.solve(circuit, M.SCIPY_LSODA)
+
+
+def test_backend_solve_batch_rabi_golden():
+    """BASELINE cfg 1 (reduced duration): Gaussian amplitude sweep vs the DOP853 truth fixture; fixed-step RK4 at
+    dt/400 is within 1e-6 of it, and B = 1 reduces to solve()."""
+    g = np.load(os.path.join(G, "rabi_gaussian_dop853.npz"))
+    h = TransmonModel.manila(extracted_qubits=[0])
+    backend = build(BackendLibrary.B200, h, ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS))
+    gate = GaussianPulseGate(duration=int(g["duration"]), amplitude=1.0)
+    B = len(g["amp"])
+    sol = backend.solve_batch(gate, {"sigma": np.full(B, float(g["sigma"]))}, PulseBackend.ODESolverMethod.QISKIT_DYNAMICS_JAX_ODEINT,
+                              amplitude=g["amp"], run_options={"rtol": 1e-11, "atol": 1e-11, "hmax": DT / 4})
+    assert np.abs(sol.states[:, -1].cpu().numpy() - g["states"][:, -1]).max() < 1e-6
+    single = backend.solve(PulseCircuit.from_pulse_gate(GaussianPulseGate(int(g["duration"]), float(g["amp"][3])), {"sigma": float(g["sigma"])}),
+                           PulseBackend.ODESolverMethod.QISKIT_DYNAMICS_JAX_ODEINT, run_options={"rtol": 1e-11, "atol": 1e-11, "hmax": DT / 4})
+    assert np.abs(single.states[-1].data - sol.states[3, -1].cpu().numpy()).max() < 1e-13
+    arr = backend.solve_batch(DragPulseGate(32, 0.3), np.array([[8.0, 1.0], [9.0, -1.0]]), PulseBackend.ODESolverMethod.QISKIT_DYNAMICS_RK4,
+                              run_options={"max_dt": DT / 40})
+    assert arr.batch_size == 2 and arr.states.shape == (2, 2, 3)
+
+
+def test_bad_arguments_raise():
+    om, nm, ch = _models((0,), "full")
+    params = engine.pack_params([dict(amp=0.5, sigma=4.0)], device="cuda")
+    with pytest.raises(CasqError, match="channel"):
+        engine.solve_sv_rk4(nm, [("gaussian", 7, 0, 16)], params, np.array([1, 0, 0]), (0, 16 * DT), DT / 40)
+    with pytest.raises(CasqError, match="max_dt"):
+        engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params, np.array([1, 0, 0]), (0, 16 * DT), 0.0)
+    with pytest.raises(CasqError, match="increasing"):
+        engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params, np.array([1, 0, 0]), (0, 16 * DT), DT / 40, [2 * DT, DT])
+    with pytest.raises(CasqError, match="y0"):
+        engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params, np.array([1, 0]), (0, 16 * DT), DT / 40)
+    with pytest.raises(CasqError, match="CUDA"):
+        engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params.cpu(), np.array([1, 0, 0]), (0, 16 * DT), DT / 40)

@@ -1,0 +1,146 @@
+"""Host-side mirror of casq's public surface (gates, circuit, models, factory): written to read like the
+reference's own unit tests (tests/casq/gates/*_test.py echo tests, backend factory tests) plus parser parity
+with the oracle's independent parser."""
+import numpy as np
+import pytest
+
+import oracle as O
+from casq_b200.backends import BackendLibrary, PulseBackend, build, build_from_backend
+from casq_b200.common.exceptions import CasqError
+from casq_b200.gates import (ConstantPulseGate, DragPulseGate, GaussianPulseGate, GaussianSquareDragPulseGate,
+                             GaussianSquarePulseGate, PulseCircuit, PulseGate)
+from casq_b200.models import ControlModel, HamiltonianModel, TransmonModel
+from casq_b200.models.hamiltonian_parser import parse_hamiltonian_dict
+
+
+def test_gaussian_pulse_gate():
+    # mirrors tests/casq/gates/gaussian_pulse_gate_test.py: parameters echo back through the pulse
+    gate = GaussianPulseGate(duration=16, amplitude=1, name="test")
+    pulse = gate.pulse({"sigma": 8})
+    assert pulse.pulse_type == "Gaussian" and pulse.duration == 16 and pulse.amp == 1 and pulse.params["sigma"] == 8
+    assert gate.to_parameters_dict(np.array([3.0])) == {"sigma": 3.0}
+    sched = gate.schedule({"sigma": 8}, 2)
+    (start, play), = sched.instructions
+    assert start == 0 and play.channel.name == "d2" and sched.duration == 16
+
+
+def test_drag_pulse_gate():
+    # mirrors tests/casq/gates/drag_pulse_gate_test.py:45-53
+    gate = DragPulseGate(duration=16, amplitude=1)
+    assert gate.angle is None  # drag_pulse_gate.py:54 default
+    pulse = gate.pulse({"sigma": 8, "beta": 2})
+    assert pulse.pulse_type == "Drag" and pulse.params == {"sigma": 8, "beta": 2} and pulse.angle == 0.0
+    assert gate.to_parameters_dict([1, 2]) == {"sigma": 1, "beta": 2}
+
+
+def test_other_gates_and_validation():
+    assert ConstantPulseGate(8, 0.5).pulse().pulse_type == "Constant"
+    assert ConstantPulseGate(8, 0.5).to_parameters_dict(np.array([])) == {}
+    gs = GaussianSquarePulseGate(32, 0.5).pulse({"sigma": 4, "width": 16})
+    assert gs.pulse_type == "GaussianSquare" and gs.params["width"] == 16
+    gsd = GaussianSquareDragPulseGate(32, 0.5)
+    assert gsd.to_parameters_dict([1, 2, 3]) == {"sigma": 1, "width": 2, "beta": 3}
+    with pytest.raises(CasqError, match="amplitude"):
+        GaussianPulseGate(16, 1.5).pulse({"sigma": 8})
+    assert GaussianPulseGate(16, 1.5, limit_amplitude=False).pulse({"sigma": 8}).amp == 1.5
+    with pytest.raises(CasqError, match="sigma"):
+        GaussianPulseGate(16, 1.0).pulse({"sigma": 0})
+    with pytest.raises(CasqError, match="width"):
+        GaussianSquarePulseGate(16, 1.0).pulse({"sigma": 2, "width": 17})
+    with pytest.raises(CasqError, match="needs parameter"):
+        DragPulseGate(16, 1.0).pulse({"sigma": 2})
+    with pytest.raises(TypeError):
+        PulseGate(1, 16, 1.0)  # abstract
+
+
+def test_pulse_circuit_from_pulse_gate():
+    gate = DragPulseGate(duration=256, amplitude=1)
+    circuit = PulseCircuit.from_pulse_gate(gate, {"sigma": 128, "beta": 2})
+    assert circuit.num_qubits == 1 and circuit.num_clbits == 1
+    assert [i.operation for i in circuit.data] == [gate, "measure"]
+    assert gate.name in circuit.calibrations and circuit.measured_qubits() == [0]
+    with pytest.raises(CasqError):
+        circuit.pulse_gate(gate, {"sigma": 1, "beta": 0}, qubit=3)
+
+
+@pytest.mark.parametrize("sub", [[0], [0, 1], [1, 3], [2, 3, 4], None])
+def test_parser_agrees_with_oracle_parser(sub):
+    a = parse_hamiltonian_dict(TransmonModel.MANILA, sub)
+    b = O.parse_hamiltonian_dict(O.MANILA, sub)
+    assert a[2] == b[2] and a[3] == b[3]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_parser_errors():
+    with pytest.raises(CasqError, match="h_str"):
+        parse_hamiltonian_dict({"qub": {"0": 2}, "vars": {}})
+    with pytest.raises(CasqError, match="unknown symbol"):
+        parse_hamiltonian_dict({"h_str": ["foo*X0"], "qub": {"0": 2}, "vars": {}})
+    with pytest.raises(CasqError, match="not in the Hamiltonian"):
+        parse_hamiltonian_dict({"h_str": ["X0"], "qub": {"0": 2}, "vars": {}}, [5])
+    st, ops, ch, dims = parse_hamiltonian_dict({"h_str": ["2*pi*(X0+Y0)/2||D0", "-w*Z0/2"], "qub": {"0": 2}, "vars": {"w": 3.0}})
+    assert ch == ["d0"] and np.allclose(st, np.diag([-1.5, 1.5])) and np.allclose(ops[0], np.pi * np.array([[0, 1 - 1j], [1 + 1j, 0]]))
+
+
+def test_transmon_model_and_frame_default_quirk():
+    P = TransmonModel.TransmonProperties
+    qm = {0: P(31179079102.853794, -2165345334.8252344, 926545606.6640488),
+          1: P(30397743782.610542, -2169482392.6367006, 892870223.8110852)}
+    full = TransmonModel(qm, {(0, 1): 11845444.218797993})
+    assert full.static_operator.shape == (9, 9) and full.channels == ["d0", "d1", "u0", "u1"]
+    assert full.extracted_qubits == [0]  # hamiltonian_model.py:78 stores [0] but parses all qubits
+    assert full.rotating_frame.shape == (9, 9)  # DENSE default -> full static operator (quirk 1)
+    one = TransmonModel(qm, {(0, 1): 11845444.218797993}, extracted_qubits=[0])
+    assert one.static_operator.shape == (3, 3) and one.channels == ["d0", "u0"]
+    diag = HamiltonianModel(TransmonModel.MANILA, extracted_qubits=[0, 1], evaluation_mode=None)
+    assert diag.rotating_frame.shape == (9,)  # raw None -> 1-D diagonal frame, mode still DENSE
+    assert diag.evaluation_mode is HamiltonianModel.EvaluationMode.DENSE
+
+
+def test_factory_and_no_cpu_fallback(native_lib):
+    import torch
+
+    h = TransmonModel.manila(extracted_qubits=[0])
+    c = ControlModel(dt=O.MANILA_DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+    with pytest.raises(ValueError, match="Unknown backend library: QISKIT"):
+        build(BackendLibrary.QISKIT, h, c)
+    with pytest.raises(ValueError, match="Unknown backend"):
+        build_from_backend(object())
+    backend = build(BackendLibrary.B200, h, c, seed=1234)
+    assert isinstance(backend, PulseBackend) and backend._seed == 1234 and backend.dim == 3
+    np.testing.assert_allclose(backend.ground_state(), [1, 0, 0])
+    with pytest.raises(CasqError, match="channel_carrier_freqs"):
+        build(BackendLibrary.B200, h, ControlModel(dt=O.MANILA_DT, channel_carrier_freqs={"d0": 5e9}))
+    circuit = PulseCircuit.from_pulse_gate(GaussianPulseGate(16, 1), {"sigma": 8})
+    sched, t_acq, measured = backend._circuit_to_schedule(circuit)
+    assert t_acq == 16 and measured == [0]
+    assert backend._slots_from_schedule(sched)[0] == [("gaussian", 0, 0, 16)]
+    if not torch.cuda.is_available():
+        with pytest.raises(CasqError, match="no CPU fallback"):
+            backend.solve(circuit, PulseBackend.ODESolverMethod.SCIPY_DOP853)
+    no_measure = PulseCircuit(1, 1)
+    no_measure.pulse_gate(GaussianPulseGate(16, 1), {"sigma": 8})
+    with pytest.raises(CasqError, match="measurement"):
+        backend._circuit_to_schedule(no_measure)
+
+
+def test_solver_method_enum_matches_casq():
+    M = PulseBackend.ODESolverMethod
+    assert {m.name: m.value for m in M} == {
+        "QISKIT_DYNAMICS_RK4": "RK4", "QISKIT_DYNAMICS_JAX_RK4": "jax_RK4", "QISKIT_DYNAMICS_JAX_ODEINT": "jax_odeint",
+        "SCIPY_BDF": "BDF", "SCIPY_DOP853": "DOP853", "SCIPY_LSODA": "LSODA", "SCIPY_RADAU": "Radau",
+        "SCIPY_RK23": "RK23", "SCIPY_RK45": "RK45"}
+    assert [m.name for m in BackendLibrary][:3] == ["C3", "QISKIT", "QUTIP"]
+
+
+def test_pack_params_layout():
+    from casq_b200 import engine
+
+    t = engine.pack_params([dict(amp=np.array([0.1, 0.2, 0.3]), angle=None, sigma=4.0, beta=np.array([1.0, 2.0, 3.0]))])
+    assert t.shape == (1, 5, 3)
+    assert t[0, 0].tolist() == [0.1, 0.2, 0.3] and t[0, 1].tolist() == [0, 0, 0] and t[0, 2].tolist() == [4, 4, 4]
+    assert t[0, 3].tolist() == [0, 0, 0] and t[0, 4].tolist() == [1, 2, 3]
+    with pytest.raises(CasqError, match="inconsistent"):
+        engine.pack_params([dict(amp=np.zeros(3), sigma=np.zeros(4))])
+    with pytest.raises(CasqError, match="unknown"):
+        engine.pack_params([dict(amp=1.0, gamma=2.0)])
