@@ -25,6 +25,7 @@
 #define SMALL_MAXD 4
 #define SMALL_MAXK 2
 #define SMALL_MAXE 6
+#define SMALL_CHUNK_STEPS 32
 
 struct SmallArgs {
   const double* table;  // [NT][W]
@@ -45,6 +46,8 @@ struct SmallArgs {
   double Pdr[SMALL_MAXK][SMALL_MAXD], Pdi[SMALL_MAXK][SMALL_MAXD];
   int identityU;
   double Ur[SMALL_MAXD][SMALL_MAXD], Ui[SMALL_MAXD][SMALL_MAXD];
+  const SmallArgs* self_dev;  // device copy of this struct (for the out-of-line slow step)
+  long long NT;               // stage-table entries
 };
 
 template <int D, bool TRI>
@@ -61,19 +64,19 @@ struct Entry {
   double Tr[KA][NE], Ti[KA][NE];
   double Nr[RWA ? KA : 1][RWA ? NE : 1], Ni[RWA ? KA : 1][RWA ? NE : 1];
 
-  __device__ __forceinline__ void load(const double* __restrict__ tab, long long pos) {
-    const double2* p = reinterpret_cast<const double2*>(tab + pos * W);
+  __device__ __forceinline__ void load(const double* __restrict__ entry) {
+    const double2* p = reinterpret_cast<const double2*>(entry);
     int o = 0;
 #pragma unroll
     for (int k = 0; k < KA; k++) {
-      double2 v = __ldg(p + o++);
+      double2 v = p[o++];
       c[k] = v.x;
       s[k] = v.y;
     }
     if (HAS_S) {
 #pragma unroll
       for (int e = 0; e < NE; e++) {
-        double2 v = __ldg(p + o++);
+        double2 v = p[o++];
         Sr[e] = v.x;
         Si[e] = v.y;
       }
@@ -82,11 +85,11 @@ struct Entry {
     for (int k = 0; k < KA; k++)
 #pragma unroll
       for (int e = 0; e < NE; e++) {
-        double2 v = __ldg(p + o++);
+        double2 v = p[o++];
         Tr[k][e] = v.x;
         Ti[k][e] = v.y;
         if (RWA) {
-          double2 w = __ldg(p + o++);
+          double2 w = p[o++];
           Nr[k][e] = w.x;
           Ni[k][e] = w.y;
         }
@@ -94,31 +97,39 @@ struct Entry {
   }
 };
 
-// k = -i H_F(t) y
+// Channel values at one stage time: zr = Re(env * carrier) (the real signal), zi = Im (RWA only).
 template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
-__device__ __forceinline__ void small_rhs(const Entry<D, KA, RWA, HAS_S, TRI>& E, const dcplx* env, const SmallArgs& a,
-                                          const double* yr, const double* yi, double* kr, double* ki) {
-  double zr[KA], zi[KA];
+__device__ __forceinline__ void small_chan(const Entry<D, KA, RWA, HAS_S, TRI>& E, const dcplx* env, double* zr, double* zi) {
 #pragma unroll
   for (int k = 0; k < KA; k++) {
     zr[k] = env[k].re * E.c[k] - env[k].im * E.s[k];
     zi[k] = RWA ? (env[k].re * E.s[k] + env[k].im * E.c[k]) : 0.0;
   }
+}
+
+// k = -i M y with M the Hermitian frame-basis Hamiltonian at this stage.  RAW = the couplings are the table
+// entries as they are (single channel, no static part): the caller folds the real signal value into the RK4
+// combination coefficients instead of scaling every coupling.  Accumulators start from their first term
+// (never from 0.0: `0.0 + x` is not foldable in IEEE arithmetic and would cost one DADD per row).
+template <int D, int KA, bool RWA, bool HAS_S, bool TRI, bool RAW>
+__device__ __forceinline__ void small_matvec(const Entry<D, KA, RWA, HAS_S, TRI>& E, const double* zr, const double* zi,
+                                             const SmallArgs& a, const double* yr, const double* yi, double* kr,
+                                             double* ki) {
   double wr[D], wi[D];
+  bool init[D];
 #pragma unroll
   for (int i = 0; i < D; i++) {
+    init[i] = false;
     if (HAS_S) {
       double h = a.Sd[i];
 #pragma unroll
       for (int k = 0; k < KA; k++) {
-        h += 2.0 * zr[k] * a.Pdr[k][i];
-        if (RWA) h -= 2.0 * zi[k] * a.Pdi[k][i];
+        h = fma(2.0 * zr[k], a.Pdr[k][i], h);
+        if (RWA) h = fma(-2.0 * zi[k], a.Pdi[k][i], h);
       }
       wr[i] = h * yr[i];
       wi[i] = h * yi[i];
-    } else {
-      wr[i] = 0.0;
-      wi[i] = 0.0;
+      init[i] = true;
     }
   }
   int e = 0;
@@ -127,37 +138,167 @@ __device__ __forceinline__ void small_rhs(const Entry<D, KA, RWA, HAS_S, TRI>& E
 #pragma unroll
     for (int j = i + 1; j < D; j++) {
       if (TRI && j != i + 1) continue;
-      double hr = HAS_S ? E.Sr[e] : 0.0, hi = HAS_S ? E.Si[e] : 0.0;
+      double hr, hi;
+      if (RAW) {
+        hr = E.Tr[0][e];
+        hi = E.Ti[0][e];
+      } else {
+        bool hinit = false;
+        if (HAS_S) {
+          hr = E.Sr[e];
+          hi = E.Si[e];
+          hinit = true;
+        }
 #pragma unroll
-      for (int k = 0; k < KA; k++) {
-        if (RWA) {
-          hr += zr[k] * (E.Tr[k][e] + E.Nr[k][e]) - zi[k] * (E.Ti[k][e] - E.Ni[k][e]);
-          hi += zr[k] * (E.Ti[k][e] + E.Ni[k][e]) + zi[k] * (E.Tr[k][e] - E.Nr[k][e]);
-        } else {
-          hr += zr[k] * E.Tr[k][e];
-          hi += zr[k] * E.Ti[k][e];
+        for (int k = 0; k < KA; k++) {
+          if (RWA) {
+            const double pr = E.Tr[k][e] + E.Nr[k][e], pi = E.Ti[k][e] + E.Ni[k][e];
+            const double mr = E.Tr[k][e] - E.Nr[k][e], mi = E.Ti[k][e] - E.Ni[k][e];
+            if (hinit) {
+              hr = fma(zr[k], pr, hr);
+              hi = fma(zr[k], pi, hi);
+            } else {
+              hr = zr[k] * pr;
+              hi = zr[k] * pi;
+              hinit = true;
+            }
+            hr = fma(-zi[k], mi, hr);
+            hi = fma(zi[k], mr, hi);
+          } else if (hinit) {
+            hr = fma(zr[k], E.Tr[k][e], hr);
+            hi = fma(zr[k], E.Ti[k][e], hi);
+          } else {
+            hr = zr[k] * E.Tr[k][e];
+            hi = zr[k] * E.Ti[k][e];
+            hinit = true;
+          }
         }
       }
       // w_i += h y_j ; w_j += conj(h) y_i
-      wr[i] += hr * yr[j] - hi * yi[j];
-      wi[i] += hr * yi[j] + hi * yr[j];
-      wr[j] += hr * yr[i] + hi * yi[i];
-      wi[j] += hr * yi[i] - hi * yr[i];
+      if (init[i]) {
+        wr[i] = fma(hr, yr[j], wr[i]);
+        wi[i] = fma(hr, yi[j], wi[i]);
+      } else {
+        wr[i] = hr * yr[j];
+        wi[i] = hr * yi[j];
+        init[i] = true;
+      }
+      wr[i] = fma(-hi, yi[j], wr[i]);
+      wi[i] = fma(hi, yr[j], wi[i]);
+      if (init[j]) {
+        wr[j] = fma(hr, yr[i], wr[j]);
+        wi[j] = fma(hr, yi[i], wi[j]);
+      } else {
+        wr[j] = hr * yr[i];
+        wi[j] = hr * yi[i];
+        init[j] = true;
+      }
+      wr[j] = fma(hi, yi[i], wr[j]);
+      wi[j] = fma(-hi, yr[i], wi[j]);
       e++;
     }
   }
 #pragma unroll
   for (int i = 0; i < D; i++) {
-    kr[i] = wi[i];
-    ki[i] = -wr[i];
+    kr[i] = init[i] ? wi[i] : 0.0;
+    ki[i] = init[i] ? -wr[i] : 0.0;
   }
 }
 
-template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
-__global__ void __launch_bounds__(64) sv_rk4_small_kernel(const SmallArgs a) {
+// One RK4 step.  REFRESH = the envelope may change between the stages of this step (the step touches a sample
+// boundary): re-evaluate it when the stage's sample index differs from the cached one.  Table entries are
+// loaded one at a time (L1-resident broadcasts; registers are the scarce resource).
+template <int D, int KA, bool RWA, bool HAS_S, bool TRI, bool REFRESH>
+__device__ __forceinline__ void small_step(const SmallArgs& a, long long b, const double* __restrict__ ent, int ia, int ib,
+                                           int ic, double h, double* yr, double* yi, dcplx* env, int& cur_idx) {
   typedef Entry<D, KA, RWA, HAS_S, TRI> Ent;
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+  constexpr bool FAST = (KA == 1 && !RWA && !HAS_S);
+  const double h2 = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+  auto env_at = [&](int gidx) {
+    if (REFRESH && gidx != cur_idx) {
+      cur_idx = gidx;
+      casq_channel_envelopes<KA>(a.slots, a.params, a.B, b, gidx, env);
+    }
+  };
+  Ent E;
+  double kr[D], ki[D], ar[D], ai[D], tr[D], ti[D], zr[KA], zi[KA];
+  // FAST: y' = s(t) * (-i T(t)) y, so u = -i T v is signal-free and s(t) rides on the combination coefficients.
+  E.load(ent);
+  env_at(ia);
+  small_chan<D, KA, RWA, HAS_S, TRI>(E, env, zr, zi);
+  small_matvec<D, KA, RWA, HAS_S, TRI, FAST>(E, zr, zi, a, yr, yi, kr, ki);
+  double c = FAST ? h2 * zr[0] : h2, g = FAST ? h6 * zr[0] : h6;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    tr[i] = fma(c, kr[i], yr[i]);
+    ti[i] = fma(c, ki[i], yi[i]);
+    ar[i] = fma(g, kr[i], yr[i]);
+    ai[i] = fma(g, ki[i], yi[i]);
+  }
+  E.load(ent + Ent::W);
+  env_at(ib);
+  small_chan<D, KA, RWA, HAS_S, TRI>(E, env, zr, zi);
+  small_matvec<D, KA, RWA, HAS_S, TRI, FAST>(E, zr, zi, a, tr, ti, kr, ki);
+  c = FAST ? h2 * zr[0] : h2;
+  g = FAST ? h3 * zr[0] : h3;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    tr[i] = fma(c, kr[i], yr[i]);
+    ti[i] = fma(c, ki[i], yi[i]);
+    ar[i] = fma(g, kr[i], ar[i]);
+    ai[i] = fma(g, ki[i], ai[i]);
+  }
+  small_matvec<D, KA, RWA, HAS_S, TRI, FAST>(E, zr, zi, a, tr, ti, kr, ki);
+  c = FAST ? h * zr[0] : h;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    tr[i] = fma(c, kr[i], yr[i]);
+    ti[i] = fma(c, ki[i], yi[i]);
+    ar[i] = fma(g, kr[i], ar[i]);
+    ai[i] = fma(g, ki[i], ai[i]);
+  }
+  E.load(ent + 2 * Ent::W);
+  env_at(ic);
+  small_chan<D, KA, RWA, HAS_S, TRI>(E, env, zr, zi);
+  small_matvec<D, KA, RWA, HAS_S, TRI, FAST>(E, zr, zi, a, tr, ti, kr, ki);
+  g = FAST ? h6 * zr[0] : h6;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    yr[i] = fma(g, kr[i], ar[i]);
+    yi[i] = fma(g, ki[i], ai[i]);
+  }
+}
+
+// A step that touches a sample boundary (about 2 in 40) goes through this out-of-line copy, which carries the
+// exp/sincos envelope code; the state crosses in local memory.  That keeps the steady-state loop of the kernel
+// a pure DFMA body with a register budget that fits 22 warps per SM.
+template <int D, int KA>
+struct SlowState {
+  double yr[D], yi[D];
+  dcplx env[KA];
+  int cur_idx;
+};
+
+template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
+__device__ __noinline__ void small_step_slow(const SmallArgs* __restrict__ ap, long long b, long long pos, int ia, int ib,
+                                             int ic, double h, SlowState<D, KA>* st) {
+  small_step<D, KA, RWA, HAS_S, TRI, true>(*ap, b, ap->table + pos * Entry<D, KA, RWA, HAS_S, TRI>::W, ia, ib, ic, h, st->yr,
+                                           st->yi, st->env, st->cur_idx);
+}
+
+// The headline shape (d<=3, one channel, nothing static in the frame) is held to 80 registers (the allocator works in 16-register steps, so 88 would still mean 20 warps/SM): 25 warps/SM, so
+// that 1e5 trajectories (3125 warps) are ONE resident wave on 148 SMs instead of a full wave plus a 17-warp tail.
+template <int D, int KA, bool RWA, bool HAS_S>
+struct SmallOcc {
+  static constexpr int kMaxRegs = (D <= 3 && KA == 1 && !RWA && !HAS_S) ? 80 : 255;
+};
+
+template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
+__global__ void __launch_bounds__(64) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>::kMaxRegs)) sv_rk4_small_kernel(const SmallArgs a) {
+  typedef Entry<D, KA, RWA, HAS_S, TRI> Ent;
+  const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = b_raw < a.B;  // dead lanes of the last block still help staging the table
+  const long long b = live ? b_raw : a.B - 1;
 
   // y <- U^+ y0
   double yr[D], yi[D];
@@ -214,69 +355,81 @@ __global__ void __launch_bounds__(64) sv_rk4_small_kernel(const SmallArgs a) {
     }
     out_slot++;
   };
-  if (a.keep[0]) emit();
+  if (a.keep[0] && live) emit();
 
   int cur_idx = -2;
   dcplx env[KA];
 #pragma unroll
   for (int k = 0; k < KA; k++) env[k].re = env[k].im = 0.0;
-  auto env_at = [&](int gidx) {
-    if (gidx != cur_idx) {  // uniform across the grid: every point shares the time grid
-      cur_idx = gidx;
-      casq_channel_envelopes<KA>(a.slots, a.params, a.B, b, gidx, env);
-    }
+
+  // The stage table is streamed through shared memory in chunks of kChunk steps, double-buffered with cp.async:
+  // all warps of an SM walk the table in near lock-step, so reading it straight from global memory made every
+  // warp wait one L2 round trip per step on the same cold line (ncu round 1: 25% long-scoreboard stalls).
+  constexpr int kChunk = SMALL_CHUNK_STEPS, kEnt = 2 * kChunk + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sm_tab0 = reinterpret_cast<double*>(smem_raw);
+  int* const sm_idx0 = reinterpret_cast<int*>(sm_tab0 + 2 * kEnt * Ent::W);
+  auto stage = [&](int buf, long long first, int n_ent) {
+    const char* src = reinterpret_cast<const char*>(a.table + first * Ent::W);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sm_tab0 + buf * (kEnt * Ent::W));
+    const int bytes = n_ent * Ent::W * 8;
+    for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off));
+    const unsigned dsti = (unsigned)__cvta_generic_to_shared(sm_idx0 + buf * (kEnt + 3));
+    for (int e = threadIdx.x; e < n_ent; e += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsti + 4 * e), "l"(a.idx + first + e));
+    asm volatile("cp.async.commit_group;");
   };
 
   long long pos = 0;
   for (int p = 0; p < a.n_pieces; p++) {
     const int n = a.piece_n[p];
     const double h = a.piece_h[p];
-    const double h2 = 0.5 * h, h6 = h * (1.0 / 6.0);
-    Ent EA, EB, EC;
-    EA.load(a.table, pos);
-    for (int s = 0; s < n; s++) {
-      EB.load(a.table, pos + 1);
-      EC.load(a.table, pos + 2);
-      const int ia = __ldg(a.idx + pos), ib = __ldg(a.idx + pos + 1), ic = __ldg(a.idx + pos + 2);
-      double kr[D], ki[D], ar[D], ai[D], tr[D], ti[D];
-      env_at(ia);
-      small_rhs<D, KA, RWA, HAS_S, TRI>(EA, env, a, yr, yi, kr, ki);
-#pragma unroll
-      for (int i = 0; i < D; i++) {
-        ar[i] = kr[i];
-        ai[i] = ki[i];
-        tr[i] = yr[i] + h2 * kr[i];
-        ti[i] = yi[i] + h2 * ki[i];
+    const int n_chunks = (n + kChunk - 1) / kChunk;
+    stage(0, pos, 2 * (n < kChunk ? n : kChunk) + 1);
+    for (int c = 0; c < n_chunks; c++) {
+      const int s0 = c * kChunk;
+      const int ns = (n - s0) < kChunk ? (n - s0) : kChunk;
+      if (c + 1 < n_chunks) {
+        const int s1 = s0 + kChunk;
+        stage((c + 1) & 1, pos + 2 * s1, 2 * ((n - s1) < kChunk ? (n - s1) : kChunk) + 1);
+        asm volatile("cp.async.wait_group 1;");
+      } else {
+        asm volatile("cp.async.wait_group 0;");
       }
-      env_at(ib);
-      small_rhs<D, KA, RWA, HAS_S, TRI>(EB, env, a, tr, ti, kr, ki);
+      __syncthreads();
+      const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
+      const int* idx = sm_idx0 + (c & 1) * (kEnt + 3);
+      for (int s = 0; s < ns; s++) {
+        const int ia = idx[2 * s], ib = idx[2 * s + 1], ic = idx[2 * s + 2];
+        // uniform across the grid: every point of the batch shares the time grid
+        if (ia == cur_idx && ib == cur_idx && ic == cur_idx) {
+          small_step<D, KA, RWA, HAS_S, TRI, false>(a, b, tab + 2 * s * Ent::W, ia, ib, ic, h, yr, yi, env, cur_idx);
+        } else {
+          SlowState<D, KA> st;
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        ar[i] += 2.0 * kr[i];
-        ai[i] += 2.0 * ki[i];
-        tr[i] = yr[i] + h2 * kr[i];
-        ti[i] = yi[i] + h2 * ki[i];
-      }
-      small_rhs<D, KA, RWA, HAS_S, TRI>(EB, env, a, tr, ti, kr, ki);
+          for (int i = 0; i < D; i++) {
+            st.yr[i] = yr[i];
+            st.yi[i] = yi[i];
+          }
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        ar[i] += 2.0 * kr[i];
-        ai[i] += 2.0 * ki[i];
-        tr[i] = yr[i] + h * kr[i];
-        ti[i] = yi[i] + h * ki[i];
-      }
-      env_at(ic);
-      small_rhs<D, KA, RWA, HAS_S, TRI>(EC, env, a, tr, ti, kr, ki);
+          for (int k = 0; k < KA; k++) st.env[k] = env[k];
+          st.cur_idx = cur_idx;
+          small_step_slow<D, KA, RWA, HAS_S, TRI>(a.self_dev, b, pos + 2 * (s0 + s), ia, ib, ic, h, &st);
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        yr[i] += h6 * (ar[i] + kr[i]);
-        yi[i] += h6 * (ai[i] + ki[i]);
+          for (int i = 0; i < D; i++) {
+            yr[i] = st.yr[i];
+            yi[i] = st.yi[i];
+          }
+#pragma unroll
+          for (int k = 0; k < KA; k++) env[k] = st.env[k];
+          cur_idx = st.cur_idx;
+        }
       }
-      EA = EC;
-      pos += 2;
+      __syncthreads();  // everyone is done with this buffer before the next-but-one chunk lands in it
     }
-    pos += 1;  // past the final time of this piece
-    if (a.keep[p + 1]) emit();
+    pos += 2LL * n + 1;  // past the final time of this piece
+    if (a.keep[p + 1] && live) emit();
   }
 }
 
@@ -330,7 +483,15 @@ template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
 static cudaError_t launch_small(const SmallArgs& a, cudaStream_t st) {
   const int block = 64;
   const long long grid = (a.B + block - 1) / block;
-  sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI><<<(unsigned)grid, block, 0, st>>>(a);
+  constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
+  const size_t smem = 2 * ((size_t)kEnt * Entry<D, KA, RWA, HAS_S, TRI>::W * sizeof(double) + (kEnt + 3) * sizeof(int));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI><<<(unsigned)grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -481,6 +642,10 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     }
   }
   a.identityU = m->U_is_identity ? 1 : 0;
+  a.NT = NT;
+  if ((rc = m->work3.ensure(sizeof(SmallArgs)))) return rc;
+  a.self_dev = (const SmallArgs*)m->work3.p;
+  CASQ_CUDA(cudaMemcpyAsync(m->work3.p, &a, sizeof(SmallArgs), cudaMemcpyHostToDevice, st));
   cudaError_t e = dispatch_small(d, KA, m->rwa, has_s, tri, a, st);
   if (e != cudaSuccess) CASQ_FAIL(CASQ_ERR_CUDA, "sv_rk4_small launch failed: %s", cudaGetErrorString(e));
   return CASQ_OK;
