@@ -10,6 +10,11 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
                    const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1, double max_dt,
                    int T, const double* t_eval, double* out_dev, cudaStream_t st);
 
+bool casq_general_supported(const casq_model* m, int n_active);
+int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& slots, int n_total, long long B,
+                     const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1, double max_dt,
+                     int T, const double* t_eval, double* out_dev, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // stand-alone envelope sampler
 __global__ void envelope_sample_kernel(int kind, int duration, long long B, const double* __restrict__ params,
@@ -88,7 +93,10 @@ extern "C" int casq_solve_sv_rk4(casq_model* m, int n_slots, const casq_pulse_sl
   if (casq_small_supported(m, n_active))
     return casq_small_rk4(m, n_active, active, ds, n_total, B, params_dev, y0_dev, y0_batched, t0, t1, max_dt, T, t_eval,
                           out_dev, (cudaStream_t)stream);
-  CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_rk4: dim %d with %d active channels has no kernel yet", m->d, n_active);
+  if (casq_general_supported(m, n_active))
+    return casq_general_rk4(m, n_active, active, ds, n_total, B, params_dev, y0_dev, y0_batched, t0, t1, max_dt, T, t_eval,
+                            out_dev, (cudaStream_t)stream);
+  CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_rk4: dim %d with %d active channels is outside the built kernels (dim <= 64, <= 4 channels)", m->d, n_active);
 }
 
 // ---------------------------------------------------------------------------------------------
