@@ -1,0 +1,415 @@
+// casq_b200: piecewise-constant propagators U = prod_n expm(h G_F(t_n + h/2)) for batches of pulse points,
+// one warp per trajectory, all matrices in shared memory (dim <= 16).
+//
+// This is the exponential-midpoint scheme of qiskit-dynamics' fixed-step "scipy_expm"/"jax_expm" solvers
+// (SURVEY.md Appendix A.5 last bullet).  casq's ODESolverMethod enum cannot select them
+// (src/casq/backends/pulse_backend.py:60-71), so this entry point is additive API for BASELINE cfg 3
+// ("2 coupled transmons (dim 9) cross-resonance GaussianSquare sweep via full-unitary propagator batches").
+// expm is the scaling-and-squaring Pade approximant of Higham (2005) -- the algorithm behind
+// jax.scipy.linalg.expm: order m in {3,5,7,9,13} chosen from ||A||_1, [m/m] Pade solved by Gaussian
+// elimination with partial pivoting, then s squarings.  d < 16 here, so this is CUDA-core complex arithmetic;
+// a split-complex tensor-core GEMM only pays for d >= 16 (north_star) and is not built.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "envelope.cuh"
+
+#define PROP_MAXK 4
+#define PROP_WARPS 4
+
+struct PropArgs {
+  const double* table;  // [NT][W]: carriers then p_i at every stage time (midpoints are the odd entries)
+  const int* idx;
+  const int* piece_n;
+  const double* piece_h;
+  int n_pieces;
+  long long B;
+  int d, KA, W, rwa;
+  const double* params;
+  double* out;  // [B][d][d] c128
+  DevSlots slots;
+  const double2* S;  // dense frame-basis operators [d*d], [KA][d*d]
+  const double2* P;
+  const double2* N;
+  int identityU;
+  const double2* U;  // frame basis
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
+  return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+// C = X * Y (d x d), warp-cooperative; C must not alias X or Y.
+__device__ __forceinline__ void wmatmul(int d, int lane, double2* C, const double2* X, const double2* Y) {
+  for (int e = lane; e < d * d; e += 32) {
+    const int i = e / d, j = e - i * d;
+    double2 acc = make_double2(0.0, 0.0);
+    for (int k = 0; k < d; k++) acc = cfma(X[i * d + k], Y[k * d + j], acc);
+    C[e] = acc;
+  }
+  __syncwarp();
+}
+
+// Solve Q X = Pm in place (X overwrites Pm); Q is destroyed.  Gaussian elimination, partial pivoting.
+__device__ void wsolve(int d, int lane, double2* Q, double2* Pm) {
+  for (int k = 0; k < d; k++) {
+    // pivot search over rows k..d-1 of column k
+    double best = -1.0;
+    int brow = k;
+    for (int r = k + lane; r < d; r += 32) {
+      const double2 v = Q[r * d + k];
+      const double mag = v.x * v.x + v.y * v.y;
+      if (mag > best) {
+        best = mag;
+        brow = r;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+      if (ob > best || (ob == best && orow < brow)) {
+        best = ob;
+        brow = orow;
+      }
+    }
+    if (brow != k) {
+      for (int j = lane; j < 2 * d; j += 32) {
+        double2* M = (j < d) ? Q : Pm;
+        const int c = (j < d) ? j : j - d;
+        const double2 t = M[k * d + c];
+        M[k * d + c] = M[brow * d + c];
+        M[brow * d + c] = t;
+      }
+      __syncwarp();
+    }
+    const double2 piv = Q[k * d + k];
+    const double inv_n = 1.0 / (piv.x * piv.x + piv.y * piv.y);
+    const double2 pinv = make_double2(piv.x * inv_n, -piv.y * inv_n);
+    __syncwarp();
+    // scale pivot row
+    for (int j = lane; j < 2 * d; j += 32) {
+      double2* M = (j < d) ? Q : Pm;
+      const int c = (j < d) ? j : j - d;
+      if (j >= d || c >= k) M[k * d + c] = cmul(M[k * d + c], pinv);
+    }
+    __syncwarp();
+    // eliminate column k from every other row (Gauss-Jordan: no back substitution pass)
+    for (int e = lane; e < d * 2 * d; e += 32) {
+      const int r = e / (2 * d), j = e - r * (2 * d);
+      if (r == k) continue;
+      double2* M = (j < d) ? Q : Pm;
+      const int c = (j < d) ? j : j - d;
+      if (j < d && c <= k) continue;  // those entries become 0/unused; the factor column is read below
+      const double2 f = Q[r * d + k];
+      const double2 p = M[k * d + c];
+      M[r * d + c] = make_double2(M[r * d + c].x - (f.x * p.x - f.y * p.y), M[r * d + c].y - (f.x * p.y + f.y * p.x));
+    }
+    __syncwarp();
+  }
+}
+
+// E = expm(A).  Workspace: A2, A4, A6, Um, Vm, T1 (each d*d).  A is overwritten (scaled).
+__device__ void wexpm(int d, int lane, double2* A, double2* E, double2* A2, double2* A4, double2* A6, double2* Um,
+                      double2* Vm, double2* T1) {
+  const int n2 = d * d;
+  // ||A||_1 = max column sum
+  double nrm = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    double s = 0.0;
+    for (int i = 0; i < d; i++) s += hypot(A[i * d + j].x, A[i * d + j].y);
+    nrm = fmax(nrm, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
+  int m, s = 0;
+  if (nrm < 1.495585217958292e-2)
+    m = 3;
+  else if (nrm < 2.539398330063230e-1)
+    m = 5;
+  else if (nrm < 9.504178996162932e-1)
+    m = 7;
+  else if (nrm < 2.097847961257068e0)
+    m = 9;
+  else {
+    m = 13;
+    const double r = nrm / 5.371920351148152e0;
+    s = r > 1.0 ? (int)ceil(log2(r)) : 0;
+    if (s > 0) {
+      const double sc = ldexp(1.0, -s);
+      for (int e = lane; e < n2; e += 32) A[e] = make_double2(A[e].x * sc, A[e].y * sc);
+      __syncwarp();
+    }
+  }
+  wmatmul(d, lane, A2, A, A);
+  auto diag = [&](int e) { return (e / d) == (e % d) ? 1.0 : 0.0; };
+  if (m == 3) {
+    const double b[4] = {120., 60., 12., 1.};
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(b[3] * A2[e].x + b[1] * diag(e), b[3] * A2[e].y);
+      Vm[e] = make_double2(b[2] * A2[e].x + b[0] * diag(e), b[2] * A2[e].y);
+    }
+  } else if (m == 5) {
+    const double b[6] = {30240., 15120., 3360., 420., 30., 1.};
+    wmatmul(d, lane, A4, A2, A2);
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e), b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  } else if (m == 7) {
+    const double b[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+    wmatmul(d, lane, A4, A2, A2);
+    wmatmul(d, lane, A6, A4, A2);
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
+                           b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
+                           b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  } else if (m == 9) {
+    const double b[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
+    wmatmul(d, lane, A4, A2, A2);
+    wmatmul(d, lane, A6, A4, A2);
+    wmatmul(d, lane, Um, A6, A2);  // A8 in Um (temporarily)
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(b[9] * Um[e].x + b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
+                           b[9] * Um[e].y + b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[8] * Um[e].x + b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
+                           b[8] * Um[e].y + b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  } else {
+    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+                          10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
+    wmatmul(d, lane, A4, A2, A2);
+    wmatmul(d, lane, A6, A4, A2);
+    // W1 = b13 A6 + b11 A4 + b9 A2 ; Z1 = b12 A6 + b10 A4 + b8 A2  (in T1 / E)
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(b[13] * A6[e].x + b[11] * A4[e].x + b[9] * A2[e].x, b[13] * A6[e].y + b[11] * A4[e].y + b[9] * A2[e].y);
+      E[e] = make_double2(b[12] * A6[e].x + b[10] * A4[e].x + b[8] * A2[e].x, b[12] * A6[e].y + b[10] * A4[e].y + b[8] * A2[e].y);
+    }
+    __syncwarp();
+    wmatmul(d, lane, Um, A6, T1);  // A6 W1
+    wmatmul(d, lane, Vm, A6, E);   // A6 Z1
+    for (int e = lane; e < n2; e += 32) {
+      T1[e] = make_double2(Um[e].x + b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
+                           Um[e].y + b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(Vm[e].x + b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
+                           Vm[e].y + b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  }
+  __syncwarp();
+  wmatmul(d, lane, Um, A, T1);  // U = A * (odd polynomial part)
+  // Q = V - U (in T1), P = V + U (in E); solve Q R = P
+  for (int e = lane; e < n2; e += 32) {
+    T1[e] = make_double2(Vm[e].x - Um[e].x, Vm[e].y - Um[e].y);
+    E[e] = make_double2(Vm[e].x + Um[e].x, Vm[e].y + Um[e].y);
+  }
+  __syncwarp();
+  wsolve(d, lane, T1, E);
+  for (int q = 0; q < s; q++) {
+    wmatmul(d, lane, T1, E, E);
+    for (int e = lane; e < n2; e += 32) E[e] = T1[e];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const PropArgs a) {
+  const int d = a.d, KA = a.KA, n2 = d * d;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_S = reinterpret_cast<double2*>(smem_raw);
+  double2* s_P = s_S + n2;
+  double2* s_N = s_P + (size_t)KA * n2;
+  double2* s_ws = s_N + (size_t)(a.rwa ? KA : 0) * n2;  // per-warp workspaces follow
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) s_S[i] = a.S[i];
+  for (int i = threadIdx.x; i < KA * n2; i += blockDim.x) {
+    s_P[i] = a.P[i];
+    if (a.rwa) s_N[i] = a.N[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b = (long long)blockIdx.x * PROP_WARPS + warp;
+  if (b >= a.B) return;
+  double2* ws = s_ws + (size_t)warp * 9 * n2;
+  double2 *A = ws, *E = ws + n2, *Uacc = ws + 2 * n2, *A2 = ws + 3 * n2, *A4 = ws + 4 * n2, *A6 = ws + 5 * n2, *Um = ws + 6 * n2,
+          *Vm = ws + 7 * n2, *T1 = ws + 8 * n2;
+  for (int e = lane; e < n2; e += 32) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
+  __syncwarp();
+
+  int cur_idx = -2;
+  dcplx env[PROP_MAXK];
+#pragma unroll
+  for (int k = 0; k < PROP_MAXK; k++) env[k].re = env[k].im = 0.0;
+
+  long long pos = 0;
+  for (int p = 0; p < a.n_pieces; p++) {
+    const int n = a.piece_n[p];
+    const double h = a.piece_h[p];
+    for (int s = 0; s < n; s++) {
+      const long long pm = pos + 1;  // midpoint entry
+      const int gidx = __ldg(a.idx + pm);
+      if (gidx != cur_idx) {
+        cur_idx = gidx;
+        casq_channel_envelopes<PROP_MAXK>(a.slots, a.params, a.B, b, gidx, env);
+      }
+      const double* ent = a.table + pm * a.W;
+      double zr[PROP_MAXK], zi[PROP_MAXK];
+#pragma unroll
+      for (int k = 0; k < PROP_MAXK; k++) {
+        if (k < KA) {
+          const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
+          zr[k] = env[k].re * c - env[k].im * sn;
+          zi[k] = env[k].re * sn + env[k].im * c;
+        } else {
+          zr[k] = zi[k] = 0.0;
+        }
+      }
+      const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
+      // A = h * (-i) * p_i conj(p_j) (S + sum_k z_k P_k + conj(z_k) N_k)
+      for (int e = lane; e < n2; e += 32) {
+        const int i = e / d, j = e - i * d;
+        double2 m = s_S[e];
+#pragma unroll
+        for (int k = 0; k < PROP_MAXK; k++) {
+          if (k < KA) {
+            const double2 P = s_P[(size_t)k * n2 + e];
+            if (a.rwa) {
+              const double2 N = s_N[(size_t)k * n2 + e];
+              m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
+              m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
+            } else {
+              m.x = fma(zr[k], P.x, m.x);
+              m.y = fma(zr[k], P.y, m.y);
+            }
+          }
+        }
+        const double2 pi_ = __ldg(ph + i), pj = __ldg(ph + j);
+        const double2 f = make_double2(pi_.x * pj.x + pi_.y * pj.y, pi_.y * pj.x - pi_.x * pj.y);  // p_i conj(p_j)
+        const double2 g = cmul(f, m);
+        A[e] = make_double2(h * g.y, -h * g.x);  // -i g
+      }
+      __syncwarp();
+      wexpm(d, lane, A, E, A2, A4, A6, Um, Vm, T1);
+      wmatmul(d, lane, T1, E, Uacc);
+      for (int e = lane; e < n2; e += 32) Uacc[e] = T1[e];
+      __syncwarp();
+      pos += 2;
+    }
+    pos += 1;
+  }
+  // out = V U V^+ (frame basis -> lab basis)
+  double2* o = reinterpret_cast<double2*>(a.out) + b * (long long)n2;
+  if (a.identityU) {
+    for (int e = lane; e < n2; e += 32) o[e] = Uacc[e];
+  } else {
+    for (int e = lane; e < n2; e += 32) {  // T1 = V U
+      const int i = e / d, j = e - i * d;
+      double2 acc = make_double2(0.0, 0.0);
+      for (int k = 0; k < d; k++) acc = cfma(__ldg(a.U + i * d + k), Uacc[k * d + j], acc);
+      T1[e] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < n2; e += 32) {
+      const int i = e / d, j = e - i * d;
+      double2 acc = make_double2(0.0, 0.0);
+      for (int k = 0; k < d; k++) {
+        const double2 v = __ldg(a.U + j * d + k);
+        acc = cfma(T1[i * d + k], make_double2(v.x, -v.y), acc);
+      }
+      o[e] = acc;
+    }
+  }
+}
+
+__global__ void sv_general_table_kernel(const double* __restrict__ times, long long NT, int KA, int d, int W,
+                                        const double* __restrict__ two_pi_nu, const double* __restrict__ fe,
+                                        double* __restrict__ out);
+int casq_prepare_slots(const casq_model* m, int n_slots, const casq_pulse_slot* slots, DevSlots* ds, int* active,
+                       int* n_active, int* n_total);
+
+extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
+                                     const double* params_dev, double t0, double t1, double max_dt, double* out_dev,
+                                     void* stream) {
+  if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: NULL model");
+  if (B < 0 || !out_dev || (n_slots > 0 && !params_dev)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: NULL buffer");
+  if (!(t1 > t0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: need t1 > t0");
+  DevSlots ds;
+  int active[CASQ_MAX_SLOTS], KA = 0, n_total = 0;
+  int rc = casq_prepare_slots(m, n_slots, slots, &ds, active, &KA, &n_total);
+  if (rc != CASQ_OK) return rc;
+  if (B == 0) return CASQ_OK;
+  if (KA == 0) {
+    if (m->K < 1) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "model without channels");
+    active[0] = 0;
+    KA = 1;
+  }
+  const int d = m->d;
+  if (d < 2 || d > 16 || KA > PROP_MAXK)
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_propagators_expm: dim %d with %d active channels is outside the built kernel (dim <= 16)", d, KA);
+  cudaStream_t st = (cudaStream_t)stream;
+  CASQ_CUDA(cudaSetDevice(m->device));
+  TimeGrid g;
+  rc = casq_build_time_grid(t0, t1, max_dt, 2, nullptr, m->dt, n_total, &g);
+  if (rc != CASQ_OK) return rc;
+  const long long NT = (long long)g.times.size();
+  const int n_pieces = (int)g.piece_nsteps.size();
+  const int W = 2 * KA + 2 * d, n2 = d * d;
+  m->tab_key.clear();
+  std::vector<double> consts(KA + d);
+  for (int k = 0; k < KA; k++) consts[k] = 2.0 * M_PI * m->nu[active[k]];
+  for (int i = 0; i < d; i++) consts[KA + i] = m->fe[i];
+  std::vector<cplx> ops((size_t)(1 + 2 * KA) * n2 + n2);
+  for (int e = 0; e < n2; e++) ops[e] = m->S[e];
+  for (int k = 0; k < KA; k++)
+    for (int e = 0; e < n2; e++) {
+      cplx p = m->P[(size_t)active[k] * n2 + e];
+      ops[(size_t)(1 + k) * n2 + e] = m->rwa ? p : 2.0 * p;
+      ops[(size_t)(1 + KA + k) * n2 + e] = m->N[(size_t)active[k] * n2 + e];
+    }
+  for (int e = 0; e < n2; e++) ops[(size_t)(1 + 2 * KA) * n2 + e] = m->U[e];
+  if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
+  if ((rc = m->tab_idx.ensure(NT * sizeof(int)))) return rc;
+  if ((rc = m->tab.ensure((size_t)NT * W * sizeof(double)))) return rc;
+  if ((rc = m->pieces_n.ensure(n_pieces * sizeof(int)))) return rc;
+  if ((rc = m->pieces_h.ensure(n_pieces * sizeof(double)))) return rc;
+  if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
+  if ((rc = m->work1.ensure(ops.size() * sizeof(cplx)))) return rc;
+  CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, g.times.data(), NT * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->pieces_n.p, g.piece_nsteps.data(), n_pieces * sizeof(int), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->pieces_h.p, g.piece_h.data(), n_pieces * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->work0.p, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->work1.p, ops.data(), ops.size() * sizeof(cplx), cudaMemcpyHostToDevice, st));
+  {
+    const long long nthreads = NT * (KA + d);
+    sv_general_table_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(
+        (const double*)m->tab_times.p, NT, KA, d, W, (const double*)m->work0.p, (const double*)m->work0.p + KA,
+        (double*)m->tab.p);
+    CASQ_CUDA(cudaGetLastError());
+  }
+  PropArgs a;
+  memset(&a, 0, sizeof(a));
+  a.table = (const double*)m->tab.p;
+  a.idx = (const int*)m->tab_idx.p;
+  a.piece_n = (const int*)m->pieces_n.p;
+  a.piece_h = (const double*)m->pieces_h.p;
+  a.n_pieces = n_pieces;
+  a.B = B;
+  a.d = d;
+  a.KA = KA;
+  a.W = W;
+  a.rwa = m->rwa ? 1 : 0;
+  a.params = params_dev;
+  a.out = out_dev;
+  a.slots = ds;
+  a.S = (const double2*)m->work1.p;
+  a.P = a.S + n2;
+  a.N = a.P + (size_t)KA * n2;
+  a.U = a.N + (size_t)KA * n2;
+  a.identityU = m->U_is_identity ? 1 : 0;
+  const size_t smem = ((size_t)(1 + KA * (m->rwa ? 2 : 1)) * n2 + (size_t)PROP_WARPS * 9 * n2) * sizeof(double2);
+  CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((B + PROP_WARPS - 1) / PROP_WARPS);
+  propagator_expm_kernel<<<grid, 32 * PROP_WARPS, smem, st>>>(a);
+  CASQ_CUDA(cudaGetLastError());
+  return CASQ_OK;
+}

@@ -159,6 +159,28 @@ def solve_sv_dopri5(model: _native.NativeModel, slots, params: torch.Tensor, y0,
     return (out, nsteps, status) if return_stats else out
 
 
+def propagators_expm(model: _native.NativeModel, slots, params: torch.Tensor, t_span, max_dt: float) -> torch.Tensor:
+    """Exponential-midpoint propagators for a batch of pulse points: CUDA complex128 [B, d, d]
+    (rotating frame, lab basis).  One expm (scaling-and-squaring Pade) per step of the fixed-step grid."""
+    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
+    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
+        raise CasqError("propagators_expm: params must be a CUDA float64 tensor [n_slots, 5, B]")
+    params = params.contiguous()
+    slots = list(slots)
+    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
+        raise CasqError(f"propagators_expm: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
+    B, d = params.shape[2], model.dim
+    out = torch.empty((B, d, d), dtype=torch.complex128, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(
+            _native.load().casq_propagators_expm(model.handle, len(slots), _native.make_slots(slots), B, params.data_ptr(),
+                                                 float(t_span[0]), float(t_span[1]), float(max_dt), out.data_ptr(),
+                                                 _stream_ptr(dev)),
+            "casq_propagators_expm",
+        )
+    return out
+
+
 def postprocess_sv(model: _native.NativeModel, times, raw: torch.Tensor, normalize: bool = True,
                    want_states: bool = True, want_probs: bool = True):
     """raw [B,T,d] (as returned by the solves) -> (states [B,T,d] lab/dressed/normalised, probs [B,T,d],

@@ -123,6 +123,17 @@ int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse_slot* slot
                          double rtol, double atol, double hmax, int64_t mxstep, int T, const double* t_eval,
                          double* out_dev, int64_t* nsteps_dev, int32_t* status_dev, void* stream);
 
+/* ---- piecewise-constant propagators ---------------------------------------------------------------
+ * casq_propagators_expm: U = prod_n expm(h G_F(t_n + h/2)), n over the fixed-step grid of [t0, t1] with
+ * h <= max_dt (same step-count rule as RK4): the exponential-midpoint scheme of qiskit-dynamics'
+ * "scipy_expm"/"jax_expm" solvers.  NOT selectable through casq's ODESolverMethod enum
+ * (src/casq/backends/pulse_backend.py:60-71) -- additive API for full-unitary sweeps (BASELINE cfg 3).
+ * expm = scaling-and-squaring Pade (Higham 2005; orders 3/5/7/9/13).  dim <= 16.
+ *   out_dev [B*dim*dim] c128: propagators in the rotating frame, lab basis (apply to the state at t0). */
+int casq_propagators_expm(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
+                          const double* params_dev, double t0, double t1, double max_dt, double* out_dev,
+                          void* stream);
+
 /* ---- result post-processing ---------------------------------------------------------------------
  * Replaces the per-time-point loop of get_experiment_result (src/casq/backends/qiskit/helpers.py:98-135)
  * for state vectors: raw_dev [B*T*dim] c128 as returned by the solves above, times host [T].
