@@ -38,6 +38,8 @@ _SIGNATURES = {
     "casq_solve_sv_dopri5": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
     "casq_propagators_expm": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, C.c_double, C.c_double, C.c_double, _P, _P]),
+    "casq_solve_lindblad_rk4": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,
+                                          C.c_double, C.c_int, _P, _P, _P, _P]),
     "casq_postprocess_sv": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "casq_fp64_fma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
 }

@@ -181,6 +181,45 @@ def propagators_expm(model: _native.NativeModel, slots, params: torch.Tensor, t_
     return out
 
 
+def solve_lindblad_rk4(model: _native.NativeModel, slots, params: torch.Tensor, rho0, t_span, max_dt: float, t_eval=None,
+                       want_rho: bool = True, want_pops: bool = True):
+    """Fixed-step RK4 of the Lindblad equation for a batch of pulse points (dissipators: model.set_dissipators).
+
+    rho0: [d] state vector, [d,d] or [B,d,d] density matrix (lab frame).  Returns (rho [B,T,d,d] in the rotating
+    frame or None, pops [B,T,d] dressed-basis populations after frame removal or None)."""
+    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
+    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
+        raise CasqError("solve_lindblad_rk4: params must be a CUDA float64 tensor [n_slots, 5, B]")
+    params = params.contiguous()
+    slots = list(slots)
+    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
+        raise CasqError(f"solve_lindblad_rk4: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
+    B, d = params.shape[2], model.dim
+    r0 = torch.as_tensor(np.asarray(rho0) if not isinstance(rho0, torch.Tensor) else rho0).to(torch.complex128)
+    if r0.shape == (d,):
+        r0 = torch.outer(r0, r0.conj())
+    if r0.shape not in ((d, d), (B, d, d)):
+        raise CasqError(f"solve_lindblad_rk4: rho0 must be [{d}], [{d},{d}] or [{B},{d},{d}], got {tuple(r0.shape)}")
+    r0 = r0.to(dev).contiguous()
+    if t_eval is None:
+        T, te = 2, None
+    else:
+        te = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
+        T = len(te)
+    rho = torch.empty((B, T, d, d), dtype=torch.complex128, device=dev) if want_rho else None
+    pops = torch.empty((B, T, d), dtype=torch.float64, device=dev) if want_pops else None
+    with torch.cuda.device(dev):
+        _native.check(
+            _native.load().casq_solve_lindblad_rk4(
+                model.handle, len(slots), _native.make_slots(slots), B, params.data_ptr(), r0.data_ptr(),
+                1 if r0.dim() == 3 else 0, float(t_span[0]), float(t_span[1]), float(max_dt), T,
+                te.ctypes.data if te is not None else None, rho.data_ptr() if rho is not None else None,
+                pops.data_ptr() if pops is not None else None, _stream_ptr(dev)),
+            "casq_solve_lindblad_rk4",
+        )
+    return rho, pops
+
+
 def postprocess_sv(model: _native.NativeModel, times, raw: torch.Tensor, normalize: bool = True,
                    want_states: bool = True, want_probs: bool = True):
     """raw [B,T,d] (as returned by the solves) -> (states [B,T,d] lab/dressed/normalised, probs [B,T,d],

@@ -134,6 +134,22 @@ int casq_propagators_expm(casq_model* m, int n_slots, const casq_pulse_slot* slo
                           const double* params_dev, double t0, double t1, double max_dt, double* out_dev,
                           void* stream);
 
+/* ---- Lindblad master equation --------------------------------------------------------------------
+ * casq_solve_lindblad_rk4: fixed-step RK4 (same stepping rule as casq_solve_sv_rk4) of
+ *   rho' = -i[H(t), rho] + sum_j (L_j rho L_j^+ - 1/2 {L_j^+ L_j, rho})
+ * in the model's rotating frame with the dissipators of casq_model_set_dissipators -- qiskit-dynamics'
+ * LindbladModel semantics; casq itself never passes dissipators (qiskit_pulse_backend.py:174-183), so this is
+ * additive API (BASELINE cfg 4).  Needs a diagonal rotating frame (frame_kind 0 or 2): the superoperator is
+ * applied in structured form in the bare tensor-product basis.
+ *   rho0_dev     [dim*dim] or [B*dim*dim] c128 (lab frame = frame at t0 = 0)
+ *   out_rho_dev  [B*T*dim*dim] c128, in the rotating frame (what Solver.solve would return), or NULL
+ *   out_pops_dev [B*T*dim] f64: populations of the dressed states after frame removal, NOT trace-normalised
+ *                (diag of V^+ e^{tF} rho e^{-tF} V, src/casq/backends/qiskit/helpers.py:110-121), or NULL */
+int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
+                            const double* params_dev, const double* rho0_dev, int rho0_batched, double t0, double t1,
+                            double max_dt, int T, const double* t_eval, double* out_rho_dev, double* out_pops_dev,
+                            void* stream);
+
 /* ---- result post-processing ---------------------------------------------------------------------
  * Replaces the per-time-point loop of get_experiment_result (src/casq/backends/qiskit/helpers.py:98-135)
  * for state vectors: raw_dev [B*T*dim] c128 as returned by the solves above, times host [T].
