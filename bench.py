@@ -36,9 +36,11 @@ DURATION, SIGMA = 256, 64.0
 T_FINAL_SAMPLES = 257
 SUBSTEPS = 40
 STEPS_PER_TRAJ = T_FINAL_SAMPLES * SUBSTEPS  # 10 280
-# Algorithmic flops of ONE RK4 step for the ladder-coupled 3-level transmon with one driven channel
-# (DESIGN.md §4): 4 x [signal 3 + 2 couplings x (2 scale + 16 matvec)] + 78 stage combinations = 234.
-FLOP_PER_STEP = 234
+# Algorithmic flops of ONE RK4 step for the ladder-coupled 3-level transmon with one driven channel, as the
+# kernel evaluates it: per stage a signal-free matvec with the two complex couplings
+# (6 mul + 10 fma = 26 flop), the real signal (3 flop) and its 1-2 coefficient products, and the fused
+# stage combinations (12 fma): 36 mul/add + 85 fma = 121 fp64 instructions = 206 flop per step.
+FLOP_PER_STEP = 206
 FLOP_PER_STEP_DENSE_MODEL = 726  # SURVEY §8(d) dense d=3,K=1 count, reported for reference only
 METRIC = "pulse trajectories/sec (d=3, S=10280 RK4 steps, fp64)"
 

@@ -55,9 +55,13 @@ class BatchSolution:
 class B200PulseBackend(PulseBackend):
     """PulseBackend whose ``solve`` runs on a B200 through libcasq_b200.so (no CPU fallback)."""
 
-    def __init__(self, hamiltonian: HamiltonianModel, control: ControlModel, seed: Optional[int] = None, device: int = 0):
+    def __init__(self, hamiltonian: HamiltonianModel, control: ControlModel, seed: Optional[int] = None, device: int = 0,
+                 noise=None):
         self._device = int(device)
+        self.noise = noise
         super().__init__(hamiltonian=hamiltonian, control=control, seed=seed)
+        if noise is not None:
+            self._native_backend.set_dissipators(noise.lindblad_operators(self.hamiltonian.qubit_dims))
 
     # ------------------------------------------------------------------ construction
     def _get_native_backend(self) -> NativeModel:
@@ -176,6 +180,32 @@ class B200PulseBackend(PulseBackend):
         states, probs, pops = engine.postprocess_sv(self._native_backend, times, raw)
         return BatchSolution(times=times, states=states, probabilities=probs, populations=pops,
                              raw=raw if keep_raw else None, nsteps=nsteps, status=status)
+
+    def solve_propagators_batch(self, slots: Sequence[tuple], slot_params: Sequence[dict], t_final: int, max_dt: float,
+                                params_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Full propagators [B, d, d] (rotating frame, lab basis) by exponential-midpoint steps of size <= max_dt:
+        the piecewise-constant path (upstream "scipy_expm"/"jax_expm"; not reachable through casq's method enum)."""
+        if params_device is None:
+            params_device = engine.pack_params(slot_params, device=torch.device("cuda", self._device))
+        return engine.propagators_expm(self._native_backend, slots, params_device, (0.0, float(t_final) * self.control.dt), max_dt)
+
+    def solve_lindblad_batch(self, slots: Sequence[tuple], slot_params: Sequence[dict], t_final: int, max_dt: float,
+                             initial_state=None, steps: Optional[int] = None, want_states: bool = False,
+                             params_device: Optional[torch.Tensor] = None):
+        """Density-matrix evolution with the backend's NoiseModel (fixed-step RK4).  Returns (times, rho [B,T,d,d] in
+        the rotating frame or None, populations [B,T,d] of the dressed states, trace-normalised like casq's
+        DensityMatrix branch, helpers.py:110-121).  Needs a diagonal rotating frame (evaluation_mode=None models)."""
+        if self.noise is None:
+            raise CasqError("solve_lindblad_batch needs a backend built with a NoiseModel (noise=...).")
+        if params_device is None:
+            params_device = engine.pack_params(slot_params, device=torch.device("cuda", self._device))
+        t_span = (0.0, float(t_final) * self.control.dt)
+        t_eval = None if steps is None else np.linspace(t_span[0], t_span[1], int(steps))
+        rho0 = self.ground_state() if initial_state is None else np.asarray(getattr(initial_state, "data", initial_state))
+        rho, pops = engine.solve_lindblad_rk4(self._native_backend, slots, params_device, rho0, t_span, max_dt, t_eval,
+                                              want_rho=want_states, want_pops=True)
+        pops = pops / pops.sum(dim=-1, keepdim=True)
+        return (np.asarray(t_span) if t_eval is None else t_eval), rho, pops
 
     def solve_batch(self, gate: PulseGate, parameters: Union[dict, np.ndarray], method: "PulseBackend.ODESolverMethod",
                     qubit: int = 0, amplitude=None, angle=None, initial_state=None, steps: Optional[int] = None,

@@ -24,10 +24,10 @@ class BackendLibrary(Enum):
 
 
 def build(backend_library: BackendLibrary, hamiltonian: HamiltonianModel, control: ControlModel,
-          seed: Optional[int] = None, device: int = 0) -> B200PulseBackend:
-    """Build a PulseBackend (same signature as casq's ``build`` plus ``device``)."""
+          seed: Optional[int] = None, device: int = 0, noise: Any = None) -> B200PulseBackend:
+    """Build a PulseBackend (same signature as casq's ``build`` plus ``device`` and an optional ``NoiseModel``)."""
     if backend_library is BackendLibrary.B200:
-        return B200PulseBackend(hamiltonian=hamiltonian, control=control, seed=seed, device=device)
+        return B200PulseBackend(hamiltonian=hamiltonian, control=control, seed=seed, device=device, noise=noise)
     raise ValueError(f"Unknown backend library: {backend_library.name}.")
 
 
