@@ -33,18 +33,23 @@
 #define LB_MAXK 4
 #define LB_THREADS 256
 
+#define LB_ELEMS 3  // tile elements per thread held in registers: TS*TS <= LB_ELEMS*LB_THREADS
+
 struct LbArgs {
-  int d, TR, TC, tiles_r, tiles_c;
+  int d, TS, nt;
   long long B;
-  int KA, NF, NTF, NQ, NU, NP, W;
+  int KA, NF, NTF, NQ, NU, NG, NP, W;
   // tables (device)
+  const int* pair_I;      // [n_pairs] tile row index  (I <= J)
+  const int* pair_J;      // [n_pairs]
   const int* q_delta;     // [NQ]
   const short* q_code;    // [NQ][d]  time-function id or -1
   const double2* q_val;   // [NQ][d]
   const int* u_delta;     // [NU]
   const short* u_code;    // [NU][d]
   const double2* u_val;   // [NU][d]
-  const int* pairs;       // [NP][2]
+  const int* grp_start;   // [NG+1] two-sided pairs grouped by (delta1, delta2): they share one gathered element
+  const int* grp_pairs;   // [NP][2]
   const int* tf_sig;      // [NTF] 0 const, 1+k: z_k, 1+KA+k: conj z_k, 1+2KA+k: Re z_k
   const int* tf_freq;     // [NTF] index into the phase part of the stage table, -1 = no phase
   const double* table;    // [NT][W]: KA carriers (cos,sin) then NF phases (cos,sin)
@@ -64,36 +69,34 @@ struct LbArgs {
 
 __device__ __forceinline__ double2 lb_cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-__global__ void __launch_bounds__(LB_THREADS) lindblad_stage_kernel(const LbArgs a) {
-  const int d = a.d, TR = a.TR, TC = a.TC, NQ = a.NQ, NU = a.NU;
+// Per-step coefficient vectors, computed ONCE per (trajectory, stage time) instead of once per tile block:
+//   cq[set][b][q][r] = value_q(r) * timefunc_q(r)(t_set)   (one-sided classes, 0 where the class does not act on row r)
+//   cu[set][b][q][r] likewise for the two-sided classes.    set 0/1/2 = t, t + h/2, t + h of this step.
+struct LbLists {        // per (set, trajectory, row) compacted class lists, written by lindblad_coef_kernel
+  int* lcnt;            // [3][B][d]       number of one-sided classes acting on the row
+  double2* lcoef;       // [3][B][d][NQ]   their coefficients
+  int* loff;            // [3][B][d][NQ]   element offset delta*d of the gathered row
+  int* gcnt;            // [3][B][d]       number of two-sided gather groups with a non-zero row factor
+  int* glist;           // [3][B][d][NG]
+};
+
+__global__ void __launch_bounds__(256) lindblad_coef_kernel(const LbArgs a, long long entry0, double2* __restrict__ cq,
+                                                            double2* __restrict__ cu, const LbLists L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_tf = reinterpret_cast<double2*>(smem_raw);   // [NTF]
-  double2* s_cL = s_tf + a.NTF;                           // [NQ][TR]
-  double2* s_cR = s_cL + NQ * TR;                         // [NQ][TC]
-  double2* s_uL = s_cR + NQ * TC;                         // [NU][TR]
-  double2* s_uR = s_uL + NU * TR;                         // [NU][TC]  (already conjugated)
-  int* s_iL = reinterpret_cast<int*>(s_uR + NU * TC);     // [NQ][TR] gathered row
-  int* s_iR = s_iL + NQ * TR;                             // [NQ][TC] gathered column
-  int* s_jL = s_iR + NQ * TC;                             // [NU][TR]
-  int* s_jR = s_jL + NU * TR;                             // [NU][TC]
+  double2* s_tf = reinterpret_cast<double2*>(smem_raw);  // [NTF]
   __shared__ dcplx s_env[LB_MAXK];
-
-  const long long b = blockIdx.y;
-  const int tile = blockIdx.x;
-  const int r0 = (tile / a.tiles_c) * TR, c0 = (tile % a.tiles_c) * TC;
-  const int nr = min(TR, d - r0), nc = min(TC, d - c0);
-  const int tid = threadIdx.x;
-
-  // (a) envelope of this trajectory at this stage's sample, (b) time functions
+  const long long b = blockIdx.x;
+  const int set = blockIdx.y, d = a.d, tid = threadIdx.x;
+  const long long entry = entry0 + set;
   if (tid == 0) {
     dcplx env[LB_MAXK];
-    casq_channel_envelopes<LB_MAXK>(a.slots, a.params, a.B, b, __ldg(a.idx + a.entry), env);
+    casq_channel_envelopes<LB_MAXK>(a.slots, a.params, a.B, b, __ldg(a.idx + entry), env);
 #pragma unroll
     for (int k = 0; k < LB_MAXK; k++) s_env[k] = env[k];
   }
   __syncthreads();
-  const double* ent = a.table + a.entry * a.W;
-  for (int n = tid; n < a.NTF; n += LB_THREADS) {
+  const double* ent = a.table + entry * a.W;
+  for (int n = tid; n < a.NTF; n += blockDim.x) {
     const int sig = a.tf_sig[n], f = a.tf_freq[n];
     double2 v = make_double2(1.0, 0.0);
     if (sig > 0) {
@@ -106,90 +109,230 @@ __global__ void __launch_bounds__(LB_THREADS) lindblad_stage_kernel(const LbArgs
     s_tf[n] = v;
   }
   __syncthreads();
-  // (c) per-tile coefficient vectors
-  for (int e = tid; e < NQ * (TR + TC); e += LB_THREADS) {
-    const int q = e / (TR + TC), l = e - q * (TR + TC);
-    const bool left = l < TR;
-    const int loc = left ? l : l - TR;
-    const int g = (left ? r0 : c0) + loc;  // global row (left) or column (right) index
-    double2 coef = make_double2(0.0, 0.0);
-    int src = g < d ? g : d - 1;
-    if (g < d) {
-      const int code = a.q_code[q * d + g];
-      if (code >= 0) {
-        coef = lb_cmul(a.q_val[q * d + g], s_tf[code]);
-        src = g + a.q_delta[q];
+  double2* oq = cq + ((long long)set * a.B + b) * a.NQ * d;
+  for (int e = tid; e < a.NQ * d; e += blockDim.x) {
+    const int code = a.q_code[e];
+    oq[e] = code >= 0 ? lb_cmul(a.q_val[e], s_tf[code]) : make_double2(0.0, 0.0);
+  }
+  double2* ou = cu + ((long long)set * a.B + b) * a.NU * d;
+  for (int e = tid; e < a.NU * d; e += blockDim.x) {
+    const int code = a.u_code[e];
+    ou[e] = code >= 0 ? lb_cmul(a.u_val[e], s_tf[code]) : make_double2(0.0, 0.0);
+  }
+  __syncthreads();  // this block wrote oq / ou itself
+  const long long rowbase = ((long long)set * a.B + b) * d;
+  for (int row = tid; row < d; row += blockDim.x) {
+    double2* lc = L.lcoef + (rowbase + row) * a.NQ;
+    int* lo = L.loff + (rowbase + row) * a.NQ;
+    int k = 0;
+    for (int q = 0; q < a.NQ; q++) {
+      const double2 c = oq[q * d + row];
+      if (c.x != 0.0 || c.y != 0.0) {
+        lc[k] = c;
+        lo[k] = a.q_delta[q] * d;
+        k++;
       }
     }
-    if (left) {
-      s_cL[q * TR + loc] = coef;
-      s_iL[q * TR + loc] = src;
-    } else {
-      s_cR[q * TC + loc] = make_double2(coef.x, -coef.y);
-      s_iR[q * TC + loc] = src;
+    L.lcnt[rowbase + row] = k;
+    int* gl = L.glist + (rowbase + row) * a.NG;
+    int gk = 0;
+    for (int g = 0; g < a.NG; g++) {
+      bool any = false;
+      for (int p = a.grp_start[g]; p < a.grp_start[g + 1]; p++) {
+        const double2 ul = ou[a.grp_pairs[2 * p] * d + row];
+        any = any || ul.x != 0.0 || ul.y != 0.0;
+      }
+      if (any) gl[gk++] = g;
+    }
+    L.gcnt[rowbase + row] = gk;
+  }
+}
+
+// rho is Hermitian, so with Lm[r,c] = sum_b alpha(r,b) rho[b,c] (left gathers only) the one-sided part is
+// Lm + Lm^+, and rho' itself is Hermitian: one block owns the tile pair (I,J),(J,I), I <= J.  The kernel is
+// LATENCY bound (each gather is an L2/DRAM round trip and a row needs 2-3 dependent batches of them), so a block
+// is 32 warps wide and every warp owns at most two tile rows (lane = column, TS <= 32): warps 0-15 compute Lm on
+// (I,J), warps 16-31 Lm on (J,I) (stored conj-transposed), then each warp finishes one row of (I,J): two-sided
+// terms, RK4 combination, write (I,J) and its conjugate mirror.  Everything that depends on the row -- which
+// classes act on it, their coefficients, the gathered row -- is warp-uniform and comes pre-compacted from
+// lindblad_coef_kernel.  (Round-1 history: v1 spent 90 % of its instructions on index arithmetic and zero tests;
+// v3 fixed that but still ran 4 rows x 3 phases serially per warp: 30 us per block whatever the batch size.)
+#define LB_STAGE_THREADS 1024
+
+__device__ __forceinline__ void lb_row_gathers(int cnt, const double2* __restrict__ lc, const int* __restrict__ lo,
+                                               const double2* __restrict__ pin, double& kx, double& ky) {
+  int k = 0;
+  for (; k + 4 <= cnt; k += 4) {
+    const double2 c0 = lc[k], c1 = lc[k + 1], c2 = lc[k + 2], c3 = lc[k + 3];
+    const double2 v0 = __ldg(pin + lo[k]), v1 = __ldg(pin + lo[k + 1]), v2 = __ldg(pin + lo[k + 2]), v3 = __ldg(pin + lo[k + 3]);
+    kx = fma(c0.x, v0.x, fma(-c0.y, v0.y, kx));
+    ky = fma(c0.x, v0.y, fma(c0.y, v0.x, ky));
+    kx = fma(c1.x, v1.x, fma(-c1.y, v1.y, kx));
+    ky = fma(c1.x, v1.y, fma(c1.y, v1.x, ky));
+    kx = fma(c2.x, v2.x, fma(-c2.y, v2.y, kx));
+    ky = fma(c2.x, v2.y, fma(c2.y, v2.x, ky));
+    kx = fma(c3.x, v3.x, fma(-c3.y, v3.y, kx));
+    ky = fma(c3.x, v3.y, fma(c3.y, v3.x, ky));
+  }
+  for (; k < cnt; k++) {
+    const double2 c0 = lc[k];
+    const double2 v0 = __ldg(pin + lo[k]);
+    kx = fma(c0.x, v0.x, fma(-c0.y, v0.y, kx));
+    ky = fma(c0.x, v0.y, fma(c0.y, v0.x, ky));
+  }
+}
+
+__global__ void __launch_bounds__(LB_STAGE_THREADS, 1) lindblad_stage_kernel(const LbArgs a, const double2* __restrict__ cu,
+                                                                            const LbLists L, int set) {
+  const int d = a.d, TS = a.TS, NQ = a.NQ, NU = a.NU, NG = a.NG;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* s_lcA = reinterpret_cast<double2*>(smem_raw);  // [TS][NQ] compacted coefficients, rows of tile I
+  double2* s_lcB = s_lcA + TS * NQ;                       // [TS][NQ] rows of tile J
+  double2* s_uL = s_lcB + TS * NQ;                        // [NU][TS] two-sided, rows of tile I
+  double2* s_uR = s_uL + NU * TS;                         // [NU][TS] two-sided, cols of tile J (conjugated)
+  double2* s_L1 = s_uR + NU * TS;                         // [TS][TS+1] Lm of tile (I,J)
+  double2* s_LT = s_L1 + TS * (TS + 1);                   // [TS][TS+1] conj-transposed Lm of tile (J,I)
+  int* s_loA = reinterpret_cast<int*>(s_LT + TS * (TS + 1));  // [TS][NQ] element offsets delta*d
+  int* s_loB = s_loA + TS * NQ;
+  int* s_cntA = s_loB + TS * NQ;  // [TS]
+  int* s_cntB = s_cntA + TS;      // [TS]
+  int* s_gl = s_cntB + TS;        // [TS][NG] groups whose row factor is non-zero
+  int* s_gcnt = s_gl + TS * NG;   // [TS]
+  int* s_goff = s_gcnt + TS;      // [NG] element offset delta1*d + delta2 of a group
+  int* s_gs = s_goff + NG;        // [NG+1] group -> pair range
+  int* s_gp = s_gs + NG + 1;      // [2*NP] class pairs
+
+  const long long b = blockIdx.y;
+  const int I = a.pair_I[blockIdx.x], J = a.pair_J[blockIdx.x];
+  const int rI = I * TS, rJ = J * TS;
+  const int nI = min(TS, d - rI), nJ = min(TS, d - rJ);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5, half = nwarps >> 1;
+
+  const long long rowbase = ((long long)set * a.B + b) * d;
+  const double2* gu = cu + ((long long)set * a.B + b) * NU * d;
+  // setup without integer divisions: warp w fetches the lists of row w of I and of J (lane = list slot)
+  for (int l = warp; l < TS; l += nwarps) {
+    const int rowA = rI + l, rowB = rJ + l;
+    const int cA = rowA < d ? L.lcnt[rowbase + rowA] : 0, cB = rowB < d ? L.lcnt[rowbase + rowB] : 0;
+    const int gA = rowA < d ? L.gcnt[rowbase + rowA] : 0;
+    if (lane < cA) {
+      s_lcA[l * NQ + lane] = L.lcoef[(rowbase + rowA) * NQ + lane];
+      s_loA[l * NQ + lane] = L.loff[(rowbase + rowA) * NQ + lane];
+    }
+    if (lane < cB) {
+      s_lcB[l * NQ + lane] = L.lcoef[(rowbase + rowB) * NQ + lane];
+      s_loB[l * NQ + lane] = L.loff[(rowbase + rowB) * NQ + lane];
+    }
+    if (lane < gA) s_gl[l * NG + lane] = L.glist[(rowbase + rowA) * NG + lane];
+    if (lane == 0) {
+      s_cntA[l] = cA;
+      s_cntB[l] = cB;
+      s_gcnt[l] = gA;
     }
   }
-  for (int e = tid; e < NU * (TR + TC); e += LB_THREADS) {
-    const int q = e / (TR + TC), l = e - q * (TR + TC);
-    const bool left = l < TR;
-    const int loc = left ? l : l - TR;
-    const int g = (left ? r0 : c0) + loc;
-    double2 coef = make_double2(0.0, 0.0);
-    int src = g < d ? g : d - 1;
-    if (g < d) {
-      const int code = a.u_code[q * d + g];
-      if (code >= 0) {
-        coef = lb_cmul(a.u_val[q * d + g], s_tf[code]);
-        src = g + a.u_delta[q];
-      }
+  for (int q = warp; q < NU; q += nwarps)
+    if (lane < TS) {
+      s_uL[q * TS + lane] = (rI + lane < d) ? gu[q * d + rI + lane] : make_double2(0.0, 0.0);
+      const double2 w = (rJ + lane < d) ? gu[q * d + rJ + lane] : make_double2(0.0, 0.0);
+      s_uR[q * TS + lane] = make_double2(w.x, -w.y);
     }
-    if (left) {
-      s_uL[q * TR + loc] = coef;
-      s_jL[q * TR + loc] = src;
-    } else {
-      s_uR[q * TC + loc] = make_double2(coef.x, -coef.y);
-      s_jR[q * TC + loc] = src;
-    }
+  if (tid <= NG) s_gs[tid] = a.grp_start[tid];
+  if (tid < 2 * a.NP) s_gp[tid] = a.grp_pairs[tid];
+  if (tid < NG) {
+    const int p0 = a.grp_start[tid];
+    s_goff[tid] = a.u_delta[a.grp_pairs[2 * p0]] * d + a.u_delta[a.grp_pairs[2 * p0 + 1]];
   }
   __syncthreads();
 
-  // (d) elements of the tile
   const double2* in = a.in + b * (long long)d * d;
+  // phase A: first half of the warps: Lm on (I,J); second half: Lm on (J,I), stored conj-transposed
+  if (warp < half) {
+    for (int rl = warp; rl < nI; rl += half)
+      if (lane < nJ) {
+        double kx = 0.0, ky = 0.0;
+        lb_row_gathers(s_cntA[rl], s_lcA + rl * NQ, s_loA + rl * NQ, in + (long long)(rI + rl) * d + rJ + lane, kx, ky);
+        s_L1[rl * (TS + 1) + lane] = make_double2(kx, ky);
+        if (I == J) s_LT[lane * (TS + 1) + rl] = make_double2(kx, -ky);
+      }
+  } else if (I != J) {
+    for (int rl = warp - half; rl < nJ; rl += half)  // row in J, lane = column in I
+      if (lane < nI) {
+        double kx = 0.0, ky = 0.0;
+        lb_row_gathers(s_cntB[rl], s_lcB + rl * NQ, s_loB + rl * NQ, in + (long long)(rJ + rl) * d + rI + lane, kx, ky);
+        s_LT[lane * (TS + 1) + rl] = make_double2(kx, -ky);
+      }
+  }
+  __syncthreads();
+  // phase B: k = Lm + Lm^+ + two-sided terms; RK4 combination; write (I,J) and its mirror
   const long long base = b * (long long)d * d;
-  for (int e = tid; e < nr * nc; e += LB_THREADS) {
-    const int rl = e / nc, cl = e - rl * nc;
-    const int r = r0 + rl, c = c0 + cl;
-    double kx = 0.0, ky = 0.0;
-    for (int q = 0; q < NQ; q++) {
-      const double2 cf = s_cL[q * TR + rl];
-      const double2 v = __ldg(in + (long long)s_iL[q * TR + rl] * d + c);
-      kx = fma(cf.x, v.x, fma(-cf.y, v.y, kx));
-      ky = fma(cf.x, v.y, fma(cf.y, v.x, ky));
-      const double2 cg = s_cR[q * TC + cl];
-      const double2 w = __ldg(in + (long long)r * d + s_iR[q * TC + cl]);
-      kx = fma(cg.x, w.x, fma(-cg.y, w.y, kx));
-      ky = fma(cg.x, w.y, fma(cg.y, w.x, ky));
-    }
-    for (int p = 0; p < a.NP; p++) {
-      const int q1 = a.pairs[2 * p], q2 = a.pairs[2 * p + 1];
-      const double2 cf = lb_cmul(s_uL[q1 * TR + rl], s_uR[q2 * TC + cl]);
-      const double2 v = __ldg(in + (long long)s_jL[q1 * TR + rl] * d + s_jR[q2 * TC + cl]);
-      kx = fma(cf.x, v.x, fma(-cf.y, v.y, kx));
-      ky = fma(cf.x, v.y, fma(cf.y, v.x, ky));
-    }
+  // one row per warp (the block has at least TS warps)
+  const int rl = warp, cl = lane;
+  const bool act = rl < nI && cl < nJ;
+  double2 l1 = make_double2(0.0, 0.0), lt = l1;
+  if (act) {
+    l1 = s_L1[rl * (TS + 1) + cl];
+    lt = s_LT[rl * (TS + 1) + cl];
+  }
+  __syncthreads();  // every (Lm, Lm^+) pair is in registers: s_L1 can take the transposed results
+  if (act) {
+    const int r = rI + rl, c = rJ + cl;
     const long long o = base + (long long)r * d + c;
+    const double2* pin = in + (long long)r * d + c;
+    // issue the epilogue loads first: they overlap the two-sided gathers
     const double2 y0 = a.y[o];
+    double2 v1 = make_double2(0.0, 0.0), v2 = v1, v3 = v1;
+    if (a.stage == 4) {
+      v1 = a.y1[o];
+      v2 = a.y2[o];
+      v3 = pin[0];
+    }
+    double kx = l1.x + lt.x, ky = l1.y + lt.y;
+    const int gc = s_gcnt[rl];
+    for (int k0 = 0; k0 < gc; k0 += 4) {
+      double cx[4], cy[4];
+      double2 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        cx[j] = cy[j] = 0.0;
+        if (k0 + j < gc) {
+          const int g = s_gl[rl * NG + k0 + j];
+          for (int p = s_gs[g]; p < s_gs[g + 1]; p++) {
+            const double2 ul = s_uL[s_gp[2 * p] * TS + rl], ur = s_uR[s_gp[2 * p + 1] * TS + cl];
+            cx[j] = fma(ul.x, ur.x, fma(-ul.y, ur.y, cx[j]));
+            cy[j] = fma(ul.x, ur.y, fma(ul.y, ur.x, cy[j]));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {  // a non-zero coefficient implies the shifted indices are valid
+        v[j] = make_double2(0.0, 0.0);
+        if (cx[j] != 0.0 || cy[j] != 0.0) v[j] = __ldg(pin + s_goff[s_gl[rl * NG + k0 + j]]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        kx = fma(cx[j], v[j].x, fma(-cy[j], v[j].y, kx));
+        ky = fma(cx[j], v[j].y, fma(cy[j], v[j].x, ky));
+      }
+    }
     double2 res;
     if (a.stage == 1 || a.stage == 2) {
       res = make_double2(fma(0.5 * a.h, kx, y0.x), fma(0.5 * a.h, ky, y0.y));
     } else if (a.stage == 3) {
       res = make_double2(fma(a.h, kx, y0.x), fma(a.h, ky, y0.y));
     } else {
-      const double2 v1 = a.y1[o], v2 = a.y2[o], v3 = in[(long long)r * d + c];
       const double t3 = 1.0 / 3.0, h6 = a.h * (1.0 / 6.0);
       res = make_double2(fma(h6, kx, t3 * (v1.x + 2.0 * v2.x + v3.x - y0.x)), fma(h6, ky, t3 * (v1.y + 2.0 * v2.y + v3.y - y0.y)));
     }
     a.out[o] = res;
+    if (I != J) s_L1[cl * (TS + 1) + rl] = make_double2(res.x, -res.y);  // own slot was consumed above; see below
+  }
+  // mirror tile (J,I): written row by row from the transposed copy so the stores are coalesced (27 lanes x 16 B
+  // contiguous) instead of 27 scattered partial-sector writes per warp
+  if (I != J) {
+    __syncthreads();
+    for (int rl = warp; rl < nJ; rl += nwarps)
+      if (lane < nI) a.out[base + (long long)(rJ + rl) * d + rI + lane] = s_L1[rl * (TS + 1) + lane];
   }
 }
 
@@ -399,15 +542,38 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const int NF = (int)bld.freqs.size(), NTF = (int)bld.tfs.size();
   if (NTF > 30000) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "too many distinct time functions (%d)", NTF);
 
-  // ---------------- tile shape: rows x cols with the coefficient vectors in <= ~96 KB of shared memory
-  int TR = std::min(d, 27), TC = std::min(d, 81);
-  auto smem_for = [&](int tr, int tc) {
-    return (size_t)NTF * 16 + (size_t)(NQ + NU) * (tr + tc) * (16 + 4) + 64;
+  // ---------------- square tiles; a block owns the tile pair (I,J),(J,I)
+  int TS = std::min(d, 27);
+  const int NG_ = std::max(1, (int)pairs.size() / 2);  // upper bound on the number of two-sided gather groups
+  auto smem_for = [&](int ts) {
+    return (size_t)(NQ + NU) * 2 * ts * 16 + 2 * (size_t)ts * (ts + 1) * 16 + ((size_t)2 * ts * NQ + 3 * ts + (size_t)ts * NG_ + 4 * NG_ + 16) * 4 + 64;
   };
-  while (smem_for(TR, TC) > 96 * 1024 && TC > 8) TC = (TC + 1) / 2;
-  while (smem_for(TR, TC) > 96 * 1024 && TR > 4) TR = (TR + 1) / 2;
-  if (smem_for(TR, TC) > 200 * 1024) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "operators too dense for the structured Lindblad kernel (%d one-sided, %d two-sided classes)", NQ, NU);
-  const int tiles_r = (d + TR - 1) / TR, tiles_c = (d + TC - 1) / TC;
+  while (smem_for(TS) > 160 * 1024 && TS > 4) TS = (TS + 1) / 2;
+  if (smem_for(TS) > 200 * 1024)
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "operators too dense for the structured Lindblad kernel (%d one-sided, %d two-sided classes)", NQ, NU);
+  const int nt = (d + TS - 1) / TS;
+  std::vector<int> pair_I, pair_J;
+  for (int I = 0; I < nt; I++)
+    for (int Jt = I; Jt < nt; Jt++) {
+      pair_I.push_back(I);
+      pair_J.push_back(Jt);
+    }
+  const int n_tile_pairs = (int)pair_I.size();
+  // group the two-sided class pairs by their shifts: members of a group gather the same rho element
+  std::vector<int> grp_start, grp_pairs;
+  {
+    std::map<std::pair<int, int>, std::vector<int>> groups;
+    for (int p = 0; p < NP; p++) groups[{us.delta[pairs[2 * p]], us.delta[pairs[2 * p + 1]]}].push_back(p);
+    grp_start.push_back(0);
+    for (auto& kv : groups) {
+      for (int p : kv.second) {
+        grp_pairs.push_back(pairs[2 * p]);
+        grp_pairs.push_back(pairs[2 * p + 1]);
+      }
+      grp_start.push_back((int)grp_pairs.size() / 2);
+    }
+  }
+  const int NG = (int)grp_start.size() - 1;
 
   // ---------------- time grid and stage table (carriers + distinct Bohr phases)
   TimeGrid g;
@@ -435,6 +601,9 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t o_ucode = off; off = align16(off + (size_t)std::max(NU, 1) * d * sizeof(short));
   const size_t o_uval = off; off = align16(off + (size_t)std::max(NU, 1) * d * 16);
   const size_t o_pairs = off; off = align16(off + std::max(NP, 1) * 2 * sizeof(int));
+  const size_t o_gstart = off; off = align16(off + (NG + 1) * sizeof(int));
+  const size_t o_pI = off; off = align16(off + n_tile_pairs * sizeof(int));
+  const size_t o_pJ = off; off = align16(off + n_tile_pairs * sizeof(int));
   const size_t o_tfsig = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_tffreq = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
@@ -448,7 +617,10 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     memcpy(&blob[o_ucode], us.code.data(), (size_t)NU * d * sizeof(short));
     memcpy(&blob[o_uval], us.val.data(), (size_t)NU * d * 16);
   }
-  if (NP) memcpy(&blob[o_pairs], pairs.data(), (size_t)NP * 2 * sizeof(int));
+  if (NP) memcpy(&blob[o_pairs], grp_pairs.data(), (size_t)NP * 2 * sizeof(int));
+  memcpy(&blob[o_gstart], grp_start.data(), (NG + 1) * sizeof(int));
+  memcpy(&blob[o_pI], pair_I.data(), n_tile_pairs * sizeof(int));
+  memcpy(&blob[o_pJ], pair_J.data(), n_tile_pairs * sizeof(int));
   if (NTF) {
     memcpy(&blob[o_tfsig], tf_sig.data(), NTF * sizeof(int));
     memcpy(&blob[o_tffreq], tf_freq.data(), NTF * sizeof(int));
@@ -462,6 +634,23 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
   if ((rc = m->work1.ensure(blob.size()))) return rc;
   if ((rc = m->work2.ensure(4 * (size_t)B * n_per * 16))) return rc;
+  const size_t n_cq = (size_t)B * NQ * d, n_cu = (size_t)B * std::max(NU, 1) * d;
+  if ((rc = m->work3.ensure(3 * (n_cq + n_cu) * 16))) return rc;
+  double2* cq_all = (double2*)m->work3.p;
+  double2* cu_all = cq_all + 3 * n_cq;
+  // compacted per-row lists (3 stage times x B x d rows)
+  const size_t n_rows = 3 * (size_t)B * d;
+  const size_t lists_bytes = n_rows * ((size_t)NQ * (16 + 4) + (size_t)std::max(NG, 1) * 4 + 8) + 64;
+  if ((rc = m->pieces_h.ensure(lists_bytes))) return rc;
+  LbLists lists;
+  {
+    unsigned char* lp = (unsigned char*)m->pieces_h.p;
+    lists.lcoef = (double2*)lp; lp += n_rows * NQ * 16;
+    lists.loff = (int*)lp; lp += n_rows * NQ * 4;
+    lists.glist = (int*)lp; lp += n_rows * std::max(NG, 1) * 4;
+    lists.lcnt = (int*)lp; lp += n_rows * 4;
+    lists.gcnt = (int*)lp;
+  }
   CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, g.times.data(), NT * sizeof(double), cudaMemcpyHostToDevice, st));
   CASQ_CUDA(cudaMemcpyAsync(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), cudaMemcpyHostToDevice, st));
   CASQ_CUDA(cudaMemcpyAsync(m->work0.p, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -483,24 +672,29 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   }
   LbArgs a;
   memset(&a, 0, sizeof(a));
-  a.d = d; a.TR = TR; a.TC = TC; a.tiles_r = tiles_r; a.tiles_c = tiles_c; a.B = B;
-  a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NP = NP; a.W = W;
+  a.d = d; a.TS = TS; a.nt = nt; a.B = B;
+  a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NG = NG; a.NP = NP; a.W = W;
+  a.pair_I = (const int*)(dev + o_pI);
+  a.pair_J = (const int*)(dev + o_pJ);
+  a.grp_start = (const int*)(dev + o_gstart);
   a.q_delta = (const int*)(dev + o_qdelta);
   a.q_code = (const short*)(dev + o_qcode);
   a.q_val = (const double2*)(dev + o_qval);
   a.u_delta = (const int*)(dev + o_udelta);
   a.u_code = (const short*)(dev + o_ucode);
   a.u_val = (const double2*)(dev + o_uval);
-  a.pairs = (const int*)(dev + o_pairs);
+  a.grp_pairs = (const int*)(dev + o_pairs);
   a.tf_sig = (const int*)(dev + o_tfsig);
   a.tf_freq = (const int*)(dev + o_tffreq);
   a.table = (const double*)m->tab.p;
   a.idx = (const int*)m->tab_idx.p;
   a.params = params_dev;
   a.slots = ds;
-  const size_t smem = smem_for(TR, TC);
+  const size_t smem = smem_for(TS);
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const dim3 grid((unsigned)(tiles_r * tiles_c), (unsigned)B);
+  const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
+  CASQ_CUDA(cudaFuncSetAttribute(lindblad_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
+  const dim3 grid((unsigned)n_tile_pairs, (unsigned)B);
   if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
 
   std::vector<cplx> ph(d);
@@ -530,15 +724,17 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     a.h = g.piece_h[p];
     for (int s = 0; s < n; s++) {
       // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
+      lindblad_coef_kernel<<<dim3((unsigned)B, 3), 256, smem_coef, st>>>(a, pos, cq_all, cu_all, lists);
       for (int stage = 1; stage <= 4; stage++) {
         a.stage = stage;
-        a.entry = pos + (stage == 1 ? 0 : (stage == 4 ? 2 : 1));
+        const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
+        a.entry = pos + set;
         a.in = bufs[stage - 1];
         a.y = bufs[0];
         a.y1 = bufs[1];
         a.y2 = bufs[2];
         a.out = stage == 4 ? bufs[0] : bufs[stage];
-        lindblad_stage_kernel<<<grid, LB_THREADS, smem, st>>>(a);
+        lindblad_stage_kernel<<<grid, LB_STAGE_THREADS, smem, st>>>(a, cu_all, lists, set);
       }
       pos += 2;
     }
