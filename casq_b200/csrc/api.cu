@@ -77,7 +77,8 @@ extern "C" int casq_solve_sv_rk4(casq_model* m, int n_slots, const casq_pulse_sl
                                  const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1,
                                  double max_dt, int T, const double* t_eval, double* out_dev, void* stream) {
   if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_rk4: NULL model");
-  if (B < 0 || !y0_dev || !out_dev || (n_slots > 0 && !params_dev)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_rk4: NULL buffer");
+  if (B < 0) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_rk4: negative batch size");
+  if (B > 0 && (!y0_dev || !out_dev || (n_slots > 0 && !params_dev))) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_rk4: NULL buffer");
   if (!(t1 > t0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_rk4: need t1 > t0");
   DevSlots ds;
   int active[CASQ_MAX_SLOTS], n_active = 0, n_total = 0;

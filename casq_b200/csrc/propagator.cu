@@ -330,7 +330,8 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
                                      const double* params_dev, double t0, double t1, double max_dt, double* out_dev,
                                      void* stream) {
   if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: NULL model");
-  if (B < 0 || !out_dev || (n_slots > 0 && !params_dev)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: NULL buffer");
+  if (B < 0) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: negative batch size");
+  if (B > 0 && (!out_dev || (n_slots > 0 && !params_dev))) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: NULL buffer");
   if (!(t1 > t0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_propagators_expm: need t1 > t0");
   DevSlots ds;
   int active[CASQ_MAX_SLOTS], KA = 0, n_total = 0;

@@ -371,7 +371,8 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
                                     double rtol, double atol, double hmax, int64_t mxstep, int T, const double* t_eval,
                                     double* out_dev, int64_t* nsteps_dev, int32_t* status_dev, void* stream) {
   if (!m) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: NULL model");
-  if (B < 0 || !y0_dev || !out_dev || (n_slots > 0 && !params_dev)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: NULL buffer");
+  if (B < 0) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: negative batch size");
+  if (B > 0 && (!y0_dev || !out_dev || (n_slots > 0 && !params_dev))) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: NULL buffer");
   if (!(t1 > t0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: need t1 > t0");
   if (!(rtol > 0) || !(atol > 0)) CASQ_FAIL(CASQ_ERR_INVALID, "casq_solve_sv_dopri5: rtol and atol must be > 0");
   DevSlots ds;
