@@ -20,370 +20,14 @@
 //     are table look-ups.  One class = one gathered rho element per side.
 //   * two-sided part: L_j rho L_j^+ [r,c] = sum over class pairs (q1,q2) of L_j of u_q1(r) conj(u_q2(c))
 //     rho[r+delta1, c+delta2].
-// Per RK4 stage ONE kernel sweeps all B density matrices: a tile of rho per block, per-tile coefficient vectors in
-// shared memory (so the inner loop is one LDS + one gathered LDG + one complex FMA per class), RK4 combination
-// fused into the epilogue (4 rolling buffers, 13 element transfers per step instead of 16).
+// Per RK4 stage: a row-wise SpMM kernel (Lm = A rho) and a combine kernel (Lm + Lm^+ + two-sided terms + fused RK4
+// combination with four rolling buffers); per step one coefficient kernel.  See lindblad_kernels.cuh.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
-#include "common.cuh"
-#include "envelope.cuh"
-
-#define LB_MAXK 4
-#define LB_THREADS 256
-
-#define LB_ELEMS 3  // tile elements per thread held in registers: TS*TS <= LB_ELEMS*LB_THREADS
-
-struct LbArgs {
-  int d, TS, nt;
-  long long B;
-  int KA, NF, NTF, NQ, NU, NG, NP, W;
-  // tables (device)
-  const int* pair_I;      // [n_pairs] tile row index  (I <= J)
-  const int* pair_J;      // [n_pairs]
-  const int* q_delta;     // [NQ]
-  const short* q_code;    // [NQ][d]  time-function id or -1
-  const double2* q_val;   // [NQ][d]
-  const int* u_delta;     // [NU]
-  const short* u_code;    // [NU][d]
-  const double2* u_val;   // [NU][d]
-  const int* grp_start;   // [NG+1] two-sided pairs grouped by (delta1, delta2): they share one gathered element
-  const int* grp_pairs;   // [NP][2]
-  const int* tf_sig;      // [NTF] 0 const, 1+k: z_k, 1+KA+k: conj z_k, 1+2KA+k: Re z_k
-  const int* tf_freq;     // [NTF] index into the phase part of the stage table, -1 = no phase
-  const double* table;    // [NT][W]: KA carriers (cos,sin) then NF phases (cos,sin)
-  const int* idx;         // [NT] sample index
-  long long entry;        // stage-table entry of this launch
-  const double* params;
-  DevSlots slots;
-  // RK4 buffers
-  const double2* in;   // stage input (gathered)
-  const double2* y;    // step start
-  const double2* y1;
-  const double2* y2;
-  double2* out;
-  int stage;  // 1..4
-  double h;
-};
-
-__device__ __forceinline__ double2 lb_cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-
-// Per-step coefficient vectors, computed ONCE per (trajectory, stage time) instead of once per tile block:
-//   cq[set][b][q][r] = value_q(r) * timefunc_q(r)(t_set)   (one-sided classes, 0 where the class does not act on row r)
-//   cu[set][b][q][r] likewise for the two-sided classes.    set 0/1/2 = t, t + h/2, t + h of this step.
-struct LbLists {        // per (set, trajectory, row) compacted class lists, written by lindblad_coef_kernel
-  int* lcnt;            // [3][B][d]       number of one-sided classes acting on the row
-  double2* lcoef;       // [3][B][d][NQ]   their coefficients
-  int* loff;            // [3][B][d][NQ]   element offset delta*d of the gathered row
-  int* gcnt;            // [3][B][d]       number of two-sided gather groups with a non-zero row factor
-  int* glist;           // [3][B][d][NG]
-};
-
-__global__ void __launch_bounds__(256) lindblad_coef_kernel(const LbArgs a, long long entry0, double2* __restrict__ cq,
-                                                            double2* __restrict__ cu, const LbLists L) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_tf = reinterpret_cast<double2*>(smem_raw);  // [NTF]
-  __shared__ dcplx s_env[LB_MAXK];
-  const long long b = blockIdx.x;
-  const int set = blockIdx.y, d = a.d, tid = threadIdx.x;
-  const long long entry = entry0 + set;
-  if (tid == 0) {
-    dcplx env[LB_MAXK];
-    casq_channel_envelopes<LB_MAXK>(a.slots, a.params, a.B, b, __ldg(a.idx + entry), env);
-#pragma unroll
-    for (int k = 0; k < LB_MAXK; k++) s_env[k] = env[k];
-  }
-  __syncthreads();
-  const double* ent = a.table + entry * a.W;
-  for (int n = tid; n < a.NTF; n += blockDim.x) {
-    const int sig = a.tf_sig[n], f = a.tf_freq[n];
-    double2 v = make_double2(1.0, 0.0);
-    if (sig > 0) {
-      const int k = (sig - 1) % a.KA, kind = (sig - 1) / a.KA;
-      const double c = ent[2 * k], s = ent[2 * k + 1];
-      const double zr = s_env[k].re * c - s_env[k].im * s, zi = s_env[k].re * s + s_env[k].im * c;
-      v = kind == 0 ? make_double2(zr, zi) : (kind == 1 ? make_double2(zr, -zi) : make_double2(zr, 0.0));
-    }
-    if (f >= 0) v = lb_cmul(v, make_double2(ent[2 * a.KA + 2 * f], ent[2 * a.KA + 2 * f + 1]));
-    s_tf[n] = v;
-  }
-  __syncthreads();
-  double2* oq = cq + ((long long)set * a.B + b) * a.NQ * d;
-  for (int e = tid; e < a.NQ * d; e += blockDim.x) {
-    const int code = a.q_code[e];
-    oq[e] = code >= 0 ? lb_cmul(a.q_val[e], s_tf[code]) : make_double2(0.0, 0.0);
-  }
-  double2* ou = cu + ((long long)set * a.B + b) * a.NU * d;
-  for (int e = tid; e < a.NU * d; e += blockDim.x) {
-    const int code = a.u_code[e];
-    ou[e] = code >= 0 ? lb_cmul(a.u_val[e], s_tf[code]) : make_double2(0.0, 0.0);
-  }
-  __syncthreads();  // this block wrote oq / ou itself
-  const long long rowbase = ((long long)set * a.B + b) * d;
-  for (int row = tid; row < d; row += blockDim.x) {
-    double2* lc = L.lcoef + (rowbase + row) * a.NQ;
-    int* lo = L.loff + (rowbase + row) * a.NQ;
-    int k = 0;
-    for (int q = 0; q < a.NQ; q++) {
-      const double2 c = oq[q * d + row];
-      if (c.x != 0.0 || c.y != 0.0) {
-        lc[k] = c;
-        lo[k] = a.q_delta[q] * d;
-        k++;
-      }
-    }
-    L.lcnt[rowbase + row] = k;
-    int* gl = L.glist + (rowbase + row) * a.NG;
-    int gk = 0;
-    for (int g = 0; g < a.NG; g++) {
-      bool any = false;
-      for (int p = a.grp_start[g]; p < a.grp_start[g + 1]; p++) {
-        const double2 ul = ou[a.grp_pairs[2 * p] * d + row];
-        any = any || ul.x != 0.0 || ul.y != 0.0;
-      }
-      if (any) gl[gk++] = g;
-    }
-    L.gcnt[rowbase + row] = gk;
-  }
-}
-
-// rho is Hermitian, so with Lm[r,c] = sum_b alpha(r,b) rho[b,c] (left gathers only) the one-sided part is
-// Lm + Lm^+, and rho' itself is Hermitian: one block owns the tile pair (I,J),(J,I), I <= J.  The kernel is
-// LATENCY bound (each gather is an L2/DRAM round trip and a row needs 2-3 dependent batches of them), so a block
-// is 32 warps wide and every warp owns at most two tile rows (lane = column, TS <= 32): warps 0-15 compute Lm on
-// (I,J), warps 16-31 Lm on (J,I) (stored conj-transposed), then each warp finishes one row of (I,J): two-sided
-// terms, RK4 combination, write (I,J) and its conjugate mirror.  Everything that depends on the row -- which
-// classes act on it, their coefficients, the gathered row -- is warp-uniform and comes pre-compacted from
-// lindblad_coef_kernel.  (Round-1 history: v1 spent 90 % of its instructions on index arithmetic and zero tests;
-// v3 fixed that but still ran 4 rows x 3 phases serially per warp: 30 us per block whatever the batch size.)
-#define LB_STAGE_THREADS 1024
-
-__device__ __forceinline__ void lb_row_gathers(int cnt, const double2* __restrict__ lc, const int* __restrict__ lo,
-                                               const double2* __restrict__ pin, double& kx, double& ky) {
-  int k = 0;
-  for (; k + 4 <= cnt; k += 4) {
-    const double2 c0 = lc[k], c1 = lc[k + 1], c2 = lc[k + 2], c3 = lc[k + 3];
-    const double2 v0 = __ldg(pin + lo[k]), v1 = __ldg(pin + lo[k + 1]), v2 = __ldg(pin + lo[k + 2]), v3 = __ldg(pin + lo[k + 3]);
-    kx = fma(c0.x, v0.x, fma(-c0.y, v0.y, kx));
-    ky = fma(c0.x, v0.y, fma(c0.y, v0.x, ky));
-    kx = fma(c1.x, v1.x, fma(-c1.y, v1.y, kx));
-    ky = fma(c1.x, v1.y, fma(c1.y, v1.x, ky));
-    kx = fma(c2.x, v2.x, fma(-c2.y, v2.y, kx));
-    ky = fma(c2.x, v2.y, fma(c2.y, v2.x, ky));
-    kx = fma(c3.x, v3.x, fma(-c3.y, v3.y, kx));
-    ky = fma(c3.x, v3.y, fma(c3.y, v3.x, ky));
-  }
-  for (; k < cnt; k++) {
-    const double2 c0 = lc[k];
-    const double2 v0 = __ldg(pin + lo[k]);
-    kx = fma(c0.x, v0.x, fma(-c0.y, v0.y, kx));
-    ky = fma(c0.x, v0.y, fma(c0.y, v0.x, ky));
-  }
-}
-
-__global__ void __launch_bounds__(LB_STAGE_THREADS, 1) lindblad_stage_kernel(const LbArgs a, const double2* __restrict__ cu,
-                                                                            const LbLists L, int set) {
-  const int d = a.d, TS = a.TS, NQ = a.NQ, NU = a.NU, NG = a.NG;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_lcA = reinterpret_cast<double2*>(smem_raw);  // [TS][NQ] compacted coefficients, rows of tile I
-  double2* s_lcB = s_lcA + TS * NQ;                       // [TS][NQ] rows of tile J
-  double2* s_uL = s_lcB + TS * NQ;                        // [NU][TS] two-sided, rows of tile I
-  double2* s_uR = s_uL + NU * TS;                         // [NU][TS] two-sided, cols of tile J (conjugated)
-  double2* s_L1 = s_uR + NU * TS;                         // [TS][TS+1] Lm of tile (I,J)
-  double2* s_LT = s_L1 + TS * (TS + 1);                   // [TS][TS+1] conj-transposed Lm of tile (J,I)
-  int* s_loA = reinterpret_cast<int*>(s_LT + TS * (TS + 1));  // [TS][NQ] element offsets delta*d
-  int* s_loB = s_loA + TS * NQ;
-  int* s_cntA = s_loB + TS * NQ;  // [TS]
-  int* s_cntB = s_cntA + TS;      // [TS]
-  int* s_gl = s_cntB + TS;        // [TS][NG] groups whose row factor is non-zero
-  int* s_gcnt = s_gl + TS * NG;   // [TS]
-  int* s_goff = s_gcnt + TS;      // [NG] element offset delta1*d + delta2 of a group
-  int* s_gs = s_goff + NG;        // [NG+1] group -> pair range
-  int* s_gp = s_gs + NG + 1;      // [2*NP] class pairs
-
-  const long long b = blockIdx.y;
-  const int I = a.pair_I[blockIdx.x], J = a.pair_J[blockIdx.x];
-  const int rI = I * TS, rJ = J * TS;
-  const int nI = min(TS, d - rI), nJ = min(TS, d - rJ);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthreads = blockDim.x, nwarps = nthreads >> 5, half = nwarps >> 1;
-
-  const long long rowbase = ((long long)set * a.B + b) * d;
-  const double2* gu = cu + ((long long)set * a.B + b) * NU * d;
-  // setup without integer divisions: warp w fetches the lists of row w of I and of J (lane = list slot)
-  for (int l = warp; l < TS; l += nwarps) {
-    const int rowA = rI + l, rowB = rJ + l;
-    const int cA = rowA < d ? L.lcnt[rowbase + rowA] : 0, cB = rowB < d ? L.lcnt[rowbase + rowB] : 0;
-    const int gA = rowA < d ? L.gcnt[rowbase + rowA] : 0;
-    if (lane < cA) {
-      s_lcA[l * NQ + lane] = L.lcoef[(rowbase + rowA) * NQ + lane];
-      s_loA[l * NQ + lane] = L.loff[(rowbase + rowA) * NQ + lane];
-    }
-    if (lane < cB) {
-      s_lcB[l * NQ + lane] = L.lcoef[(rowbase + rowB) * NQ + lane];
-      s_loB[l * NQ + lane] = L.loff[(rowbase + rowB) * NQ + lane];
-    }
-    if (lane < gA) s_gl[l * NG + lane] = L.glist[(rowbase + rowA) * NG + lane];
-    if (lane == 0) {
-      s_cntA[l] = cA;
-      s_cntB[l] = cB;
-      s_gcnt[l] = gA;
-    }
-  }
-  for (int q = warp; q < NU; q += nwarps)
-    if (lane < TS) {
-      s_uL[q * TS + lane] = (rI + lane < d) ? gu[q * d + rI + lane] : make_double2(0.0, 0.0);
-      const double2 w = (rJ + lane < d) ? gu[q * d + rJ + lane] : make_double2(0.0, 0.0);
-      s_uR[q * TS + lane] = make_double2(w.x, -w.y);
-    }
-  if (tid <= NG) s_gs[tid] = a.grp_start[tid];
-  if (tid < 2 * a.NP) s_gp[tid] = a.grp_pairs[tid];
-  if (tid < NG) {
-    const int p0 = a.grp_start[tid];
-    s_goff[tid] = a.u_delta[a.grp_pairs[2 * p0]] * d + a.u_delta[a.grp_pairs[2 * p0 + 1]];
-  }
-  __syncthreads();
-
-  const double2* in = a.in + b * (long long)d * d;
-  // phase A: first half of the warps: Lm on (I,J); second half: Lm on (J,I), stored conj-transposed
-  if (warp < half) {
-    for (int rl = warp; rl < nI; rl += half)
-      if (lane < nJ) {
-        double kx = 0.0, ky = 0.0;
-        lb_row_gathers(s_cntA[rl], s_lcA + rl * NQ, s_loA + rl * NQ, in + (long long)(rI + rl) * d + rJ + lane, kx, ky);
-        s_L1[rl * (TS + 1) + lane] = make_double2(kx, ky);
-        if (I == J) s_LT[lane * (TS + 1) + rl] = make_double2(kx, -ky);
-      }
-  } else if (I != J) {
-    for (int rl = warp - half; rl < nJ; rl += half)  // row in J, lane = column in I
-      if (lane < nI) {
-        double kx = 0.0, ky = 0.0;
-        lb_row_gathers(s_cntB[rl], s_lcB + rl * NQ, s_loB + rl * NQ, in + (long long)(rJ + rl) * d + rI + lane, kx, ky);
-        s_LT[lane * (TS + 1) + rl] = make_double2(kx, -ky);
-      }
-  }
-  __syncthreads();
-  // phase B: k = Lm + Lm^+ + two-sided terms; RK4 combination; write (I,J) and its mirror
-  const long long base = b * (long long)d * d;
-  // one row per warp (the block has at least TS warps)
-  const int rl = warp, cl = lane;
-  const bool act = rl < nI && cl < nJ;
-  double2 l1 = make_double2(0.0, 0.0), lt = l1;
-  if (act) {
-    l1 = s_L1[rl * (TS + 1) + cl];
-    lt = s_LT[rl * (TS + 1) + cl];
-  }
-  __syncthreads();  // every (Lm, Lm^+) pair is in registers: s_L1 can take the transposed results
-  if (act) {
-    const int r = rI + rl, c = rJ + cl;
-    const long long o = base + (long long)r * d + c;
-    const double2* pin = in + (long long)r * d + c;
-    // issue the epilogue loads first: they overlap the two-sided gathers
-    const double2 y0 = a.y[o];
-    double2 v1 = make_double2(0.0, 0.0), v2 = v1, v3 = v1;
-    if (a.stage == 4) {
-      v1 = a.y1[o];
-      v2 = a.y2[o];
-      v3 = pin[0];
-    }
-    double kx = l1.x + lt.x, ky = l1.y + lt.y;
-    const int gc = s_gcnt[rl];
-    for (int k0 = 0; k0 < gc; k0 += 4) {
-      double cx[4], cy[4];
-      double2 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        cx[j] = cy[j] = 0.0;
-        if (k0 + j < gc) {
-          const int g = s_gl[rl * NG + k0 + j];
-          for (int p = s_gs[g]; p < s_gs[g + 1]; p++) {
-            const double2 ul = s_uL[s_gp[2 * p] * TS + rl], ur = s_uR[s_gp[2 * p + 1] * TS + cl];
-            cx[j] = fma(ul.x, ur.x, fma(-ul.y, ur.y, cx[j]));
-            cy[j] = fma(ul.x, ur.y, fma(ul.y, ur.x, cy[j]));
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {  // a non-zero coefficient implies the shifted indices are valid
-        v[j] = make_double2(0.0, 0.0);
-        if (cx[j] != 0.0 || cy[j] != 0.0) v[j] = __ldg(pin + s_goff[s_gl[rl * NG + k0 + j]]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        kx = fma(cx[j], v[j].x, fma(-cy[j], v[j].y, kx));
-        ky = fma(cx[j], v[j].y, fma(cy[j], v[j].x, ky));
-      }
-    }
-    double2 res;
-    if (a.stage == 1 || a.stage == 2) {
-      res = make_double2(fma(0.5 * a.h, kx, y0.x), fma(0.5 * a.h, ky, y0.y));
-    } else if (a.stage == 3) {
-      res = make_double2(fma(a.h, kx, y0.x), fma(a.h, ky, y0.y));
-    } else {
-      const double t3 = 1.0 / 3.0, h6 = a.h * (1.0 / 6.0);
-      res = make_double2(fma(h6, kx, t3 * (v1.x + 2.0 * v2.x + v3.x - y0.x)), fma(h6, ky, t3 * (v1.y + 2.0 * v2.y + v3.y - y0.y)));
-    }
-    a.out[o] = res;
-    if (I != J) s_L1[cl * (TS + 1) + rl] = make_double2(res.x, -res.y);  // own slot was consumed above; see below
-  }
-  // mirror tile (J,I): written row by row from the transposed copy so the stores are coalesced (27 lanes x 16 B
-  // contiguous) instead of 27 scattered partial-sector writes per warp
-  if (I != J) {
-    __syncthreads();
-    for (int rl = warp; rl < nJ; rl += nwarps)
-      if (lane < nI) a.out[base + (long long)(rJ + rl) * d + rI + lane] = s_L1[rl * (TS + 1) + lane];
-  }
-}
-
-// rho0 broadcast / copy into the working buffer
-__global__ void lindblad_init_kernel(long long n_per, long long B, const double2* __restrict__ rho0, int batched,
-                                     double2* __restrict__ y) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_per * B) return;
-  y[i] = batched ? rho0[i] : rho0[i % n_per];
-}
-
-// Observables at one output time: dressed-basis populations p_i = (V^+ rho_lab V)_ii with
-// rho_lab[a,b] = e^{-i(e_a-e_b)t} rho_F[a,b].  One block per (state i, trajectory b).
-__global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, const double2* __restrict__ rho, const double2* __restrict__ V,
-                                                            const double2* __restrict__ ph /*[d] e^{-i e t}*/,
-                                                            double* __restrict__ pops, int T, int t_slot) {
-  const int i = blockIdx.x;
-  const long long b = blockIdx.y;
-  const double2* R = rho + b * (long long)d * d;
-  __shared__ double red[256];
-  double acc = 0.0;
-  // sum_{a,b'} conj(V[a,i]) ph_a rho[a,b'] conj(ph_b') V[b',i]  (real for Hermitian rho)
-  for (int arow = threadIdx.x; arow < d; arow += blockDim.x) {
-    double sx = 0.0, sy = 0.0;
-    for (int bc = 0; bc < d; bc++) {
-      const double2 v = V[bc * d + i], p = ph[bc];
-      const double2 w = make_double2(v.x * p.x + v.y * p.y, v.y * p.x - v.x * p.y);  // V[b,i] conj(ph_b)
-      const double2 x = R[(long long)arow * d + bc];
-      sx += x.x * w.x - x.y * w.y;
-      sy += x.x * w.y + x.y * w.x;
-    }
-    const double2 va = V[arow * d + i], pa = ph[arow];
-    const double2 l = make_double2(va.x * pa.x + va.y * pa.y, va.x * pa.y - va.y * pa.x);  // conj(V[a,i]) ph_a
-    acc += l.x * sx - l.y * sy;
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) pops[(b * T + t_slot) * (long long)d + i] = red[0];
-}
-
-__global__ void lindblad_copy_out_kernel(long long n_per, long long B, const double2* __restrict__ y, double2* __restrict__ out,
-                                         int T, int t_slot) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_per * B) return;
-  const long long b = i / n_per, e = i - b * n_per;
-  out[(b * T + t_slot) * n_per + e] = y[i];
-}
+#include "lindblad_kernels.cuh"
 
 __global__ void sv_general_table_kernel(const double* __restrict__ times, long long NT, int KA, int d, int W,
                                         const double* __restrict__ two_pi_nu, const double* __restrict__ fe,
@@ -542,30 +186,40 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const int NF = (int)bld.freqs.size(), NTF = (int)bld.tfs.size();
   if (NTF > 30000) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "too many distinct time functions (%d)", NTF);
 
-  // ---------------- square tiles; a block owns the tile pair (I,J),(J,I)
-  int TS = std::min(d, 27);
-  const int NG_ = std::max(1, (int)pairs.size() / 2);  // upper bound on the number of two-sided gather groups
-  auto smem_for = [&](int ts) {
-    return (size_t)(NQ + NU) * 2 * ts * 16 + 2 * (size_t)ts * (ts + 1) * 16 + ((size_t)2 * ts * NQ + 3 * ts + (size_t)ts * NG_ + 4 * NG_ + 16) * 4 + 64;
-  };
-  while (smem_for(TS) > 160 * 1024 && TS > 4) TS = (TS + 1) / 2;
-  if (smem_for(TS) > 200 * 1024)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "operators too dense for the structured Lindblad kernel (%d one-sided, %d two-sided classes)", NQ, NU);
-  const int nt = (d + TS - 1) / TS;
-  std::vector<int> pair_I, pair_J;
-  for (int I = 0; I < nt; I++)
-    for (int Jt = I; Jt < nt; Jt++) {
-      pair_I.push_back(I);
-      pair_J.push_back(Jt);
-    }
-  const int n_tile_pairs = (int)pair_I.size();
   // group the two-sided class pairs by their shifts: members of a group gather the same rho element
   std::vector<int> grp_start, grp_pairs;
+  std::vector<cplx> cdense;  // [d*d] folded constant diagonal two-sided coefficients (already x 1/2), or empty
   {
     std::map<std::pair<int, int>, std::vector<int>> groups;
     for (int p = 0; p < NP; p++) groups[{us.delta[pairs[2 * p]], us.delta[pairs[2 * p + 1]]}].push_back(p);
     grp_start.push_back(0);
     for (auto& kv : groups) {
+      // A group that gathers the element itself (delta1 = delta2 = 0) with time-independent factors (e.g. the five
+      // pure-dephasing operators n_q) is folded into ONE dense constant coefficient matrix: 1 load instead of 1 per pair.
+      if (kv.first.first == 0 && kv.first.second == 0) {
+        bool constant = true;
+        for (int p : kv.second)
+          for (int side = 0; side < 2 && constant; side++) {
+            const int q = pairs[2 * p + side];
+            for (int r = 0; r < d && constant; r++) {
+              const int code = us.code[(size_t)q * d + r];
+              if (code >= 0 && (bld.tfs[code].first != 0 || bld.tfs[code].second != -1)) constant = false;
+            }
+          }
+        if (constant) {
+          if (cdense.empty()) cdense.assign((size_t)d * d, cplx(0.0));
+          for (int p : kv.second) {
+            const int q1 = pairs[2 * p], q2 = pairs[2 * p + 1];
+            for (int r = 0; r < d; r++) {
+              if (us.code[(size_t)q1 * d + r] < 0) continue;
+              const cplx ul = 0.5 * us.val[(size_t)q1 * d + r];
+              for (int c = 0; c < d; c++)
+                if (us.code[(size_t)q2 * d + c] >= 0) cdense[(size_t)r * d + c] += ul * std::conj(us.val[(size_t)q2 * d + c]);
+            }
+          }
+          continue;
+        }
+      }
       for (int p : kv.second) {
         grp_pairs.push_back(pairs[2 * p]);
         grp_pairs.push_back(pairs[2 * p + 1]);
@@ -602,12 +256,11 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t o_uval = off; off = align16(off + (size_t)std::max(NU, 1) * d * 16);
   const size_t o_pairs = off; off = align16(off + std::max(NP, 1) * 2 * sizeof(int));
   const size_t o_gstart = off; off = align16(off + (NG + 1) * sizeof(int));
-  const size_t o_pI = off; off = align16(off + n_tile_pairs * sizeof(int));
-  const size_t o_pJ = off; off = align16(off + n_tile_pairs * sizeof(int));
   const size_t o_tfsig = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_tffreq = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
   const size_t o_ph = off; off = align16(off + (size_t)d * 16);
+  const size_t o_cd = off; off = align16(off + (cdense.empty() ? 16 : (size_t)d * d * 16));
   std::vector<unsigned char> blob(off, 0);
   memcpy(&blob[o_qdelta], os.delta.data(), NQ * sizeof(int));
   memcpy(&blob[o_qcode], os.code.data(), (size_t)NQ * d * sizeof(short));
@@ -617,15 +270,14 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     memcpy(&blob[o_ucode], us.code.data(), (size_t)NU * d * sizeof(short));
     memcpy(&blob[o_uval], us.val.data(), (size_t)NU * d * 16);
   }
-  if (NP) memcpy(&blob[o_pairs], grp_pairs.data(), (size_t)NP * 2 * sizeof(int));
+  if (!grp_pairs.empty()) memcpy(&blob[o_pairs], grp_pairs.data(), grp_pairs.size() * sizeof(int));
   memcpy(&blob[o_gstart], grp_start.data(), (NG + 1) * sizeof(int));
-  memcpy(&blob[o_pI], pair_I.data(), n_tile_pairs * sizeof(int));
-  memcpy(&blob[o_pJ], pair_J.data(), n_tile_pairs * sizeof(int));
   if (NTF) {
     memcpy(&blob[o_tfsig], tf_sig.data(), NTF * sizeof(int));
     memcpy(&blob[o_tffreq], tf_freq.data(), NTF * sizeof(int));
   }
   memcpy(&blob[o_V], m->V.data(), (size_t)d * d * 16);
+  if (!cdense.empty()) memcpy(&blob[o_cd], cdense.data(), (size_t)d * d * 16);
 
   const size_t n_per = (size_t)d * d;
   if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
@@ -633,7 +285,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   if ((rc = m->tab.ensure((size_t)NT * std::max(W, 2) * sizeof(double)))) return rc;
   if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
   if ((rc = m->work1.ensure(blob.size()))) return rc;
-  if ((rc = m->work2.ensure(4 * (size_t)B * n_per * 16))) return rc;
+  if (NQ > LB_MAXQ) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "more than %d one-sided shift classes (%d): operators too dense for the structured path", LB_MAXQ, NQ);
+  if ((rc = m->work2.ensure(5 * (size_t)B * n_per * 16))) return rc;
   const size_t n_cq = (size_t)B * NQ * d, n_cu = (size_t)B * std::max(NU, 1) * d;
   if ((rc = m->work3.ensure(3 * (n_cq + n_cu) * 16))) return rc;
   double2* cq_all = (double2*)m->work3.p;
@@ -663,8 +316,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     CASQ_CUDA(cudaGetLastError());
   }
   unsigned char* dev = (unsigned char*)m->work1.p;
-  double2* bufs[4];
-  for (int i = 0; i < 4; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_per;
+  double2* bufs[5];  // y, y1, y2, y3, Lm
+  for (int i = 0; i < 5; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_per;
   {
     const long long n = (long long)B * n_per;
     lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)n_per, B, (const double2*)rho0_dev, rho0_batched, bufs[0]);
@@ -672,10 +325,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   }
   LbArgs a;
   memset(&a, 0, sizeof(a));
-  a.d = d; a.TS = TS; a.nt = nt; a.B = B;
-  a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NG = NG; a.NP = NP; a.W = W;
-  a.pair_I = (const int*)(dev + o_pI);
-  a.pair_J = (const int*)(dev + o_pJ);
+  a.d = d; a.B = B;
+  a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NG = NG; a.NP = (int)grp_pairs.size() / 2; a.W = W;
   a.grp_start = (const int*)(dev + o_gstart);
   a.q_delta = (const int*)(dev + o_qdelta);
   a.q_code = (const short*)(dev + o_qcode);
@@ -690,12 +341,16 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   a.idx = (const int*)m->tab_idx.p;
   a.params = params_dev;
   a.slots = ds;
-  const size_t smem = smem_for(TS);
-  CASQ_CUDA(cudaFuncSetAttribute(lindblad_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.cdense = cdense.empty() ? nullptr : (const double2*)(dev + o_cd);
+  if (NU > LB_MAXQ || NG > LB_MAXQ || 2 * NP > 4 * LB_MAXQ)
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "too many two-sided classes for the structured Lindblad kernel (%d classes, %d pairs)", NU, NP);
   const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
-  const dim3 grid((unsigned)n_tile_pairs, (unsigned)B);
   if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
+  const int nt32 = (d + 31) / 32;
+  const dim3 grid_spmm((unsigned)((d + 7) / 8), (unsigned)B), grid_comb((unsigned)(nt32 * nt32), (unsigned)B);
+  int nch = d <= 32 ? 1 : (d <= 64 ? 2 : 4);  // 4 chunks x 2 passes beats 8 x 1 at d = 243: registers buy occupancy, the kernel is latency bound
+  if (const char* env = getenv("CASQ_LB_NCH")) nch = atoi(env);  // tuning knob: column chunks of 32 held in registers per pass
 
   std::vector<cplx> ph(d);
   int t_slot = 0;
@@ -721,20 +376,29 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   long long pos = 0;
   for (size_t p = 0; p < g.piece_nsteps.size(); p++) {
     const int n = g.piece_nsteps[p];
-    a.h = g.piece_h[p];
+    const double h_piece = g.piece_h[p];
     for (int s = 0; s < n; s++) {
       // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
       lindblad_coef_kernel<<<dim3((unsigned)B, 3), 256, smem_coef, st>>>(a, pos, cq_all, cu_all, lists);
+      // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
       for (int stage = 1; stage <= 4; stage++) {
-        a.stage = stage;
         const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
-        a.entry = pos + set;
-        a.in = bufs[stage - 1];
-        a.y = bufs[0];
-        a.y1 = bufs[1];
-        a.y2 = bufs[2];
-        a.out = stage == 4 ? bufs[0] : bufs[stage];
-        lindblad_stage_kernel<<<grid, LB_STAGE_THREADS, smem, st>>>(a, cu_all, lists, set);
+        LbStage sg;
+        sg.in = bufs[stage - 1];
+        sg.lm = bufs[4];
+        sg.y = bufs[0];
+        sg.y1 = bufs[1];
+        sg.y2 = bufs[2];
+        sg.out = stage == 4 ? bufs[0] : bufs[stage];
+        sg.stage = stage;
+        sg.h = h_piece;
+        switch (nch) {
+          case 1: lindblad_spmm_kernel<1><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
+          case 2: lindblad_spmm_kernel<2><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
+          case 4: lindblad_spmm_kernel<4><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
+          default: lindblad_spmm_kernel<8><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
+        }
+        lindblad_combine_kernel<<<grid_comb, dim3(32, 8), 0, st>>>(d, sg);
       }
       pos += 2;
     }
