@@ -57,3 +57,25 @@ class DensityMatrix(_State):
 
     def __repr__(self):
         return f"DensityMatrix(dim={self.dim}, dims={self._dims})"
+
+
+def populations_by_qubit(probabilities, dims: Sequence[int], measured: Optional[Sequence[int]] = None) -> dict:
+    """Outcome populations with every level >= 1 of each measured subsystem clipped to "1" -- what
+    ``_get_memory_slot_probabilities(..., max_outcome_value=1)`` yields when ``subsystem_dims`` IS forwarded (casq does
+    not forward it, src/casq/backends/qiskit/qiskit_pulse_backend.py:184-188, so its multi-qubit populations fold
+    everything into one pseudo-qubit: SURVEY §5 quirk 2).  Bit-strings are big-endian in the measured list (slot 0
+    right-most).  ``probabilities`` is one level-probability vector [prod(dims)] (numpy or torch)."""
+    p = np.asarray(probabilities.cpu() if hasattr(probabilities, "cpu") else probabilities, dtype=float)
+    dims = list(dims)
+    if p.shape != (int(np.prod(dims)),):
+        raise ValueError(f"need {int(np.prod(dims))} probabilities, got {p.shape}")
+    measured = list(range(len(dims))) if measured is None else list(measured)
+    out: dict = {}
+    for idx, val in enumerate(p):
+        levels, rem = [], idx
+        for dim in dims:  # subsystem 0 is the least-significant digit
+            levels.append(rem % dim)
+            rem //= dim
+        key = "".join(str(min(levels[q], 1)) for q in reversed(measured))
+        out[key] = out.get(key, 0.0) + float(val)
+    return out

@@ -316,3 +316,19 @@ def test_bad_arguments_raise():
         engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params, np.array([1, 0]), (0, 16 * DT), DT / 40)
     with pytest.raises(CasqError, match="CUDA"):
         engine.solve_sv_rk4(nm, [("gaussian", 0, 0, 16)], params.cpu(), np.array([1, 0, 0]), (0, 16 * DT), DT / 40)
+
+
+def test_discretize_matches_oracle_signals():
+    """casq.common.helpers.discretize: per-channel sampled signals with I/Q components (helpers.py:105-144)."""
+    from casq_b200.common import discretize
+    from casq_b200.gates import GaussianSquareDragPulseGate
+
+    gate = GaussianSquareDragPulseGate(duration=40, amplitude=0.6, angle=0.4)
+    sched = gate.schedule({"sigma": 5.0, "width": 12.0, "beta": 1.5}, 0)
+    sigs = discretize(sched, DT, {"d0": 4.96e9, "u0": 4.84e9})
+    assert [s.name for s in sigs] == ["d0", "u0"] and sigs[0].duration == 40 and sigs[0].carrier == 4.96e9
+    want = O.envelope_samples("gaussian_square_drag", 40, amp=0.6, angle=0.4, sigma=5.0, width=12.0, beta=1.5)
+    assert np.abs(sigs[0].signal.samples - want).max() < 1e-14
+    assert np.abs(sigs[0].q_signal.samples - (want.imag - 1j * want.real)).max() < 1e-14
+    assert sigs[0].i_signal.carrier_freq == pytest.approx(2 * 4.96e9) and not sigs[1].signal.samples.any()
+    assert discretize(sched, DT, {"d0": 4.96e9}, carrier_frequency=1e8)[0].carrier == 1e8

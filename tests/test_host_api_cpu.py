@@ -144,3 +144,25 @@ def test_pack_params_layout():
         engine.pack_params([dict(amp=np.zeros(3), sigma=np.zeros(4))])
     with pytest.raises(CasqError, match="unknown"):
         engine.pack_params([dict(amp=1.0, gamma=2.0)])
+
+
+def test_decorators_and_per_qubit_populations(caplog):
+    import logging
+
+    from casq_b200.common import timer, trace
+    from casq_b200.quantum_info import populations_by_qubit
+
+    @trace(level="DEBUG")
+    @timer(level="DEBUG", unit="msec")
+    def f(x, y=2):
+        return x + y
+
+    with caplog.at_level(logging.DEBUG, logger="casq_b200"):
+        assert f(1, y=3) == 4
+    text = caplog.text
+    assert "Entering [f" in text and "Exiting [f] with result [4]" in text and "milliseconds" in text
+    two = populations_by_qubit(np.full(9, 1 / 9), [3, 3])
+    assert two == pytest.approx({"00": 1 / 9, "01": 2 / 9, "10": 2 / 9, "11": 4 / 9})
+    assert two == pytest.approx(O.populations_dict(np.full(9, 1 / 9), subsystem_dims=[3, 3], measured=(0, 1)))
+    one = populations_by_qubit(np.array([0.5, 0.25, 0.25, 0, 0, 0, 0, 0, 0]), [3, 3], measured=[0])
+    assert one == pytest.approx({"0": 0.5, "1": 0.5})
