@@ -16,6 +16,7 @@
 //    changes -- once per ~40 steps -- from the per-point parameters (amp, angle, sigma, width, beta).
 //  * operator sparsity is a compile-time property of the instantiation (TRI = tridiagonal ladder coupling,
 //    HAS_S = static/diagonal terms survive in the frame), so absent elements cost neither registers nor flops.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -294,7 +295,7 @@ struct SmallOcc {
 };
 
 template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
-__global__ void __launch_bounds__(64) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>::kMaxRegs)) sv_rk4_small_kernel(const SmallArgs a) {
+__global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>::kMaxRegs)) sv_rk4_small_kernel(const SmallArgs a) {
   typedef Entry<D, KA, RWA, HAS_S, TRI> Ent;
   const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = b_raw < a.B;  // dead lanes of the last block still help staging the table
@@ -481,7 +482,9 @@ __global__ void sv_table_kernel(const TableArgs a) {
 // ---------------------------------------------------------------------------------------------
 template <int D, int KA, bool RWA, bool HAS_S, bool TRI>
 static cudaError_t launch_small(const SmallArgs& a, cudaStream_t st) {
-  const int block = 64;
+  int block = 64;
+  if (const char* env = getenv("CASQ_SMALL_BLOCK")) block = atoi(env);  // tuning knob (32, 64 or 128 threads)
+  if (block != 32 && block != 64 && block != 128) block = 64;
   const long long grid = (a.B + block - 1) / block;
   constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
   const size_t smem = 2 * ((size_t)kEnt * Entry<D, KA, RWA, HAS_S, TRI>::W * sizeof(double) + (kEnt + 3) * sizeof(int));
