@@ -365,6 +365,11 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
 
 int casq_prepare_slots(const casq_model* m, int n_slots, const casq_pulse_slot* slots, DevSlots* ds, int* active,
                        int* n_active, int* n_total);
+bool casq_dopri5_general_supported(const casq_model* m, int n_active);
+int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots& slots, int n_total, long long B,
+                        const double* params_dev, const double* y0_dev, int y0_batched, double rtol, double atol, double hmax,
+                        long long mxstep, const std::vector<double>& pts, const std::vector<char>& keep, int T_out,
+                        double* out_dev, long long* nsteps_dev, int* status_dev, cudaStream_t st);
 
 extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
                                     const double* params_dev, const double* y0_dev, int y0_batched, double t0, double t1,
@@ -386,8 +391,9 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     KA = 1;
   }
   const int d = m->d;
-  if (d < 2 || d > DP_MAXD || KA > DP_MAXK)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: dim %d with %d active channels has no kernel yet", d, KA);
+  const bool small_path = d >= 2 && d <= DP_MAXD && KA <= DP_MAXK;
+  if (!small_path && !casq_dopri5_general_supported(m, KA))
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: dim %d with %d active channels is outside the built kernels (dim <= 64, <= 4 channels)", d, KA);
   cudaStream_t st = (cudaStream_t)stream;
   CASQ_CUDA(cudaSetDevice(m->device));
 
@@ -417,6 +423,10 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     }
   }
   const int TM = (int)pts.size();
+  if (!small_path)
+    return casq_dopri5_general(m, KA, active, ds, n_total, B, params_dev, y0_dev, y0_batched, rtol, atol,
+                               (hmax > 0) ? hmax : INFINITY, (mxstep > 0) ? (long long)mxstep : (1LL << 62), pts, keep, T, out_dev,
+                               (long long*)nsteps_dev, status_dev, st);
   if ((rc = m->tab_times.ensure(TM * sizeof(double)))) return rc;
   if ((rc = m->consts.ensure(TM))) return rc;
   m->tab_key.clear();  // the fixed-step table cache shares these buffers

@@ -78,3 +78,60 @@ def test_three_transmons_d27_and_five_level():
     _, want = O.rk4_solve(om5, samples, y0, (0.0, 20 * DT), DT / 40)
     got = engine.solve_sv_rk4(nm5, [("gaussian", 0, 0, 20)], engine.pack_params(ps, device="cuda"), y0, (0.0, 20 * DT), DT / 40).cpu().numpy()
     assert np.abs(got - want).max() < TOL_STATE
+
+
+def test_dopri5_general_d9_smooth_is_step_exact_and_sampled_within_tolerance():
+    """Adaptive Dopri5 on the 2-transmon model (warp-per-trajectory kernel): same controller, same decisions on a
+    smooth right-hand side; with sampled envelopes agreement at the controller's own accuracy (see test_gpu_parity_sv)."""
+    rng = np.random.default_rng(31)
+    om, nm, ch = _pair(O.MANILA, [0, 1], "full", None)
+    B = 3
+    p = dict(amp=rng.uniform(0.2, 0.7, B), angle=rng.uniform(-1, 1, B))
+    samples = O.channel_samples(ch, [O.PulseSpec("constant", "u0", 30)], [p])
+    y0 = rng.normal(size=(B, 9)) + 1j * rng.normal(size=(B, 9))
+    y0 /= np.linalg.norm(y0, axis=1, keepdims=True)
+    span = (0.0, 16 * DT)
+    te = np.linspace(0, 16 * DT, 4)
+    _, want, steps = O.dopri5_jax_solve(om, samples, y0, span, te, rtol=1e-8, atol=1e-8)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("constant", ch.index("u0"), 0, 30)], engine.pack_params([p], device="cuda"), y0, span,
+                                             rtol=1e-8, atol=1e-8, t_eval=te, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-11
+    # sampled envelopes, RWA, diagonal frame, two channels
+    om, nm, ch = _pair(O.MANILA, [0, 1], "diag", 3.0e9)
+    specs = [O.PulseSpec("gaussian_square", "u0", 24), O.PulseSpec("drag", "d1", 16, start=4)]
+    ps = [dict(amp=rng.uniform(0.1, 0.6, B), angle=0.2, sigma=4.0, width=10.0), dict(amp=rng.uniform(0.1, 0.4, B), angle=0.0, sigma=3.0, beta=1.0)]
+    samples = O.channel_samples(ch, specs, ps)
+    y0 = np.zeros(9, dtype=complex)
+    y0[0] = 1
+    span = (0.0, 24 * DT)
+    _, want, steps = O.dopri5_jax_solve(om, samples, y0, span, rtol=1e-9, atol=1e-9)
+    slots = [("gaussian_square", ch.index("u0"), 0, 24), ("drag", ch.index("d1"), 4, 16)]
+    got, ns, status = engine.solve_sv_dopri5(nm, slots, engine.pack_params(ps, device="cuda"), y0, span, rtol=1e-9, atol=1e-9, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.abs(got.cpu().numpy() - want).max() < 5e-6
+    assert np.abs(ns.cpu().numpy() - steps).max() <= 0.05 * steps.max()
+
+
+def test_backend_solve_two_qubit_model_all_methods():
+    """The drop-in call on a d = 9 model: fixed-step and adaptive methods both run (general-dimension kernels)."""
+    from casq_b200.backends import BackendLibrary, PulseBackend, build
+    from casq_b200.gates import GaussianPulseGate, PulseCircuit
+    from casq_b200.models import ControlModel, TransmonModel
+
+    h = TransmonModel.manila(extracted_qubits=[0, 1])
+    backend = build(BackendLibrary.B200, h, ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS), seed=5)
+    assert backend.dim == 9
+    circuit = PulseCircuit.from_pulse_gate(GaussianPulseGate(duration=32, amplitude=0.4), {"sigma": 8.0})
+    om, _, ch = _pair(O.MANILA, [0, 1], "full", None)
+    ref = O.casq_solve(om, [O.PulseSpec("gaussian", "d0", 32)], [dict(amp=0.4, angle=0.0, sigma=8.0)], method="RK4", steps=3,
+                       run_options={"max_dt": DT / 40})
+    M = PulseBackend.ODESolverMethod
+    sol = backend.solve(circuit, M.QISKIT_DYNAMICS_RK4, steps=3, run_options={"max_dt": DT / 40})
+    got = np.array([s.data for s in sol.states])
+    assert got.shape == (3, 9) and np.abs(got - ref["states"][0]).max() < 1e-9
+    truth = O.casq_solve(om, [O.PulseSpec("gaussian", "d0", 32)], [dict(amp=0.4, angle=0.0, sigma=8.0)], method="DOP853",
+                         run_options={"rtol": 1e-11, "atol": 1e-11})["states"][0, -1]
+    for m in (M.QISKIT_DYNAMICS_JAX_ODEINT, M.SCIPY_RK45):
+        s2 = backend.solve(circuit, m, run_options={"rtol": 1e-10, "atol": 1e-10})
+        assert np.abs(s2.states[-1].data - truth).max() < 1e-5
+        assert set(s2.populations[-1]) <= {"0", "1"} and sum(s2.counts[-1].values()) == 1024
