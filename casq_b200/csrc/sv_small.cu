@@ -49,6 +49,7 @@ struct SmallArgs {
   double Ur[SMALL_MAXD][SMALL_MAXD], Ui[SMALL_MAXD][SMALL_MAXD];
   const SmallArgs* self_dev;  // device copy of this struct (for the out-of-line slow step)
   long long NT;               // stage-table entries
+  const unsigned* fast_mask;  // one word per 32-step chunk (see the kernel)
 };
 
 template <int D, bool TRI>
@@ -369,20 +370,17 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
   constexpr int kChunk = SMALL_CHUNK_STEPS, kEnt = 2 * kChunk + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* const sm_tab0 = reinterpret_cast<double*>(smem_raw);
-  int* const sm_idx0 = reinterpret_cast<int*>(sm_tab0 + 2 * kEnt * Ent::W);
   auto stage = [&](int buf, long long first, int n_ent) {
     const char* src = reinterpret_cast<const char*>(a.table + first * Ent::W);
     const unsigned dst = (unsigned)__cvta_generic_to_shared(sm_tab0 + buf * (kEnt * Ent::W));
     const int bytes = n_ent * Ent::W * 8;
     for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off));
-    const unsigned dsti = (unsigned)__cvta_generic_to_shared(sm_idx0 + buf * (kEnt + 3));
-    for (int e = threadIdx.x; e < n_ent; e += blockDim.x)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsti + 4 * e), "l"(a.idx + first + e));
     asm volatile("cp.async.commit_group;");
   };
 
   long long pos = 0;
+  long long mask_pos = 0;  // fast-step masks: one 32-bit word per chunk, pieces back to back
   for (int p = 0; p < a.n_pieces; p++) {
     const int n = a.piece_n[p];
     const double h = a.piece_h[p];
@@ -400,13 +398,16 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
       }
       __syncthreads();
       const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
-      const int* idx = sm_idx0 + (c & 1) * (kEnt + 3);
+      // bit s = "all three stage times of step s lie in the sample the envelope was last evaluated for": decided
+      // once on the host (the time grid is shared by the whole batch), so the steady-state step starts without a
+      // load -> compare -> branch chain
+      const unsigned fast = __ldg(a.fast_mask + mask_pos + c);
       for (int s = 0; s < ns; s++) {
-        const int ia = idx[2 * s], ib = idx[2 * s + 1], ic = idx[2 * s + 2];
-        // uniform across the grid: every point of the batch shares the time grid
-        if (ia == cur_idx && ib == cur_idx && ic == cur_idx) {
-          small_step<D, KA, RWA, HAS_S, TRI, false>(a, b, tab + 2 * s * Ent::W, ia, ib, ic, h, yr, yi, env, cur_idx);
+        if ((fast >> s) & 1u) {
+          small_step<D, KA, RWA, HAS_S, TRI, false>(a, b, tab + 2 * s * Ent::W, cur_idx, cur_idx, cur_idx, h, yr, yi, env, cur_idx);
         } else {
+          const long long gp = pos + 2 * (s0 + s);
+          const int ia = __ldg(a.idx + gp), ib = __ldg(a.idx + gp + 1), ic = __ldg(a.idx + gp + 2);
           SlowState<D, KA> st;
 #pragma unroll
           for (int i = 0; i < D; i++) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
 #pragma unroll
           for (int k = 0; k < KA; k++) st.env[k] = env[k];
           st.cur_idx = cur_idx;
-          small_step_slow<D, KA, RWA, HAS_S, TRI>(a.self_dev, b, pos + 2 * (s0 + s), ia, ib, ic, h, &st);
+          small_step_slow<D, KA, RWA, HAS_S, TRI>(a.self_dev, b, gp, ia, ib, ic, h, &st);
 #pragma unroll
           for (int i = 0; i < D; i++) {
             yr[i] = st.yr[i];
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
       __syncthreads();  // everyone is done with this buffer before the next-but-one chunk lands in it
     }
     pos += 2LL * n + 1;  // past the final time of this piece
+    mask_pos += n_chunks;
     if (a.keep[p + 1] && live) emit();
   }
 }
@@ -487,7 +489,7 @@ static cudaError_t launch_small(const SmallArgs& a, cudaStream_t st) {
   if (block != 32 && block != 64 && block != 128) block = 64;
   const long long grid = (a.B + block - 1) / block;
   constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
-  const size_t smem = 2 * ((size_t)kEnt * Entry<D, KA, RWA, HAS_S, TRI>::W * sizeof(double) + (kEnt + 3) * sizeof(int));
+  const size_t smem = 2 * (size_t)kEnt * Entry<D, KA, RWA, HAS_S, TRI>::W * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -570,6 +572,27 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     if (t_eval) key.append(reinterpret_cast<const char*>(t_eval), sizeof(double) * T);
   }
   std::vector<char> keep(g.out_keep.begin(), g.out_keep.end());
+  // fast-step masks: simulate the envelope cache (cur) over the shared time grid
+  std::vector<unsigned> masks;
+  {
+    int cur = -2;
+    long long p0 = 0;
+    for (int p = 0; p < n_pieces; p++) {
+      const int n = g.piece_nsteps[p];
+      for (int s0 = 0; s0 < n; s0 += SMALL_CHUNK_STEPS) {
+        unsigned w = 0;
+        for (int s = s0; s < n && s < s0 + SMALL_CHUNK_STEPS; s++) {
+          const int ia = g.sample_idx[p0 + 2 * s], ib = g.sample_idx[p0 + 2 * s + 1], ic = g.sample_idx[p0 + 2 * s + 2];
+          if (ia == cur && ib == cur && ic == cur)
+            w |= 1u << (s - s0);
+          else
+            cur = ic;
+        }
+        masks.push_back(w);
+      }
+      p0 += 2LL * n + 1;
+    }
+  }
   if (key != m->tab_key) {
     m->tab_key.clear();
     if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
@@ -578,6 +601,8 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     if ((rc = m->pieces_n.ensure(n_pieces * sizeof(int)))) return rc;
     if ((rc = m->pieces_h.ensure(n_pieces * sizeof(double)))) return rc;
     if ((rc = m->consts.ensure(keep.size()))) return rc;
+    if ((rc = m->work2.ensure(masks.size() * sizeof(unsigned)))) return rc;
+    CASQ_CUDA(cudaMemcpyAsync(m->work2.p, masks.data(), masks.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
     CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, g.times.data(), NT * sizeof(double), cudaMemcpyHostToDevice, st));
     CASQ_CUDA(cudaMemcpyAsync(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), cudaMemcpyHostToDevice, st));
     CASQ_CUDA(cudaMemcpyAsync(m->pieces_n.p, g.piece_nsteps.data(), n_pieces * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -646,6 +671,7 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
   }
   a.identityU = m->U_is_identity ? 1 : 0;
   a.NT = NT;
+  a.fast_mask = (const unsigned*)m->work2.p;
   if ((rc = m->work3.ensure(sizeof(SmallArgs)))) return rc;
   a.self_dev = (const SmallArgs*)m->work3.p;
   CASQ_CUDA(cudaMemcpyAsync(m->work3.p, &a, sizeof(SmallArgs), cudaMemcpyHostToDevice, st));
