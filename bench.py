@@ -314,7 +314,7 @@ def run_ours(args) -> None:
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
-                         "kernel": "sv_rk4_small_kernel<3,1,noRWA,noS,TRI>", "kernel_ms": ms_kernel,
+                         "kernel": "sv_rk4_small2_kernel<3,TRI> (2 trajectories per thread)", "kernel_ms": ms_kernel,
                          "flop_per_step": FLOP_PER_STEP, "dense_model_flop_per_step": FLOP_PER_STEP_DENSE_MODEL,
                          "peak_source": "measured live: casq_fp64_fma_probe (MEASURED_PEAKS.json has no fp64 entry)"},
             "cpu_baseline": cpu,

@@ -437,6 +437,218 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two trajectories per thread for the headline shape (one channel, nothing static in the frame): the two
+// RK4 chains are independent, so every stage offers twice the instruction-level parallelism to the fp64 pipe
+// while the table entry (shared by the whole batch) is loaded once for both.  Same arithmetic, same order per
+// trajectory as sv_rk4_small_kernel.
+template <int D, bool TRI>
+__global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
+  typedef Entry<D, 1, false, false, TRI> Ent;
+  const long long half = (a.B + 1) / 2;
+  const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live0 = t_raw < half;
+  const long long b0 = live0 ? t_raw : half - 1;
+  const bool live1 = live0 && (b0 + half) < a.B;
+  const long long b1 = live1 ? b0 + half : b0;
+
+  double y0r[D], y0i[D], y1r[D], y1i[D];
+  auto init = [&](long long b, double* yr, double* yi) {
+    const double* src = a.y0 + (a.y0_batched ? b * 2 * D : 0);
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double sr = 0, si = 0;
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        const double ur = a.identityU ? (i == j ? 1.0 : 0.0) : a.Ur[j][i];
+        const double ui = a.identityU ? 0.0 : a.Ui[j][i];
+        sr += ur * src[2 * j] + ui * src[2 * j + 1];
+        si += ur * src[2 * j + 1] - ui * src[2 * j];
+      }
+      yr[i] = sr;
+      yi[i] = si;
+    }
+  };
+  init(b0, y0r, y0i);
+  init(b1, y1r, y1i);
+  int out_slot = 0;
+  auto emit_one = [&](long long b, const double* yr, const double* yi) {
+    double* o = a.out + (b * (long long)a.T + out_slot) * 2 * D;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      double sr = 0, si = 0;
+#pragma unroll
+      for (int j = 0; j < D; j++) {
+        const double ur = a.identityU ? (i == j ? 1.0 : 0.0) : a.Ur[i][j];
+        const double ui = a.identityU ? 0.0 : a.Ui[i][j];
+        sr += ur * yr[j] - ui * yi[j];
+        si += ur * yi[j] + ui * yr[j];
+      }
+      o[2 * i] = sr;
+      o[2 * i + 1] = si;
+    }
+  };
+  auto emit = [&]() {
+    if (live0) emit_one(b0, y0r, y0i);
+    if (live1) emit_one(b1, y1r, y1i);
+    out_slot++;
+  };
+  if (a.keep[0]) emit();
+
+  int cur_idx = -2;
+  dcplx env0, env1;
+  env0.re = env0.im = env1.re = env1.im = 0.0;
+
+  constexpr int kChunk = SMALL_CHUNK_STEPS, kEnt = 2 * kChunk + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* const sm_tab0 = reinterpret_cast<double*>(smem_raw);
+  auto stage = [&](int buf, long long first, int n_ent) {
+    const char* src = reinterpret_cast<const char*>(a.table + first * Ent::W);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sm_tab0 + buf * (kEnt * Ent::W));
+    const int bytes = n_ent * Ent::W * 8;
+    for (int off = threadIdx.x * 16; off < bytes; off += blockDim.x * 16)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off));
+    asm volatile("cp.async.commit_group;");
+  };
+  // one RK4 stage for both trajectories: k = -i T v (signal-free), signal folded into the coefficients by the caller
+  auto matvec2 = [&](const Ent& E, const double* v0r, const double* v0i, const double* v1r, const double* v1i, double* k0r,
+                     double* k0i, double* k1r, double* k1i) {
+    double zz[1] = {0.0};
+    small_matvec<D, 1, false, false, TRI, true>(E, zz, zz, a, v0r, v0i, k0r, k0i);
+    small_matvec<D, 1, false, false, TRI, true>(E, zz, zz, a, v1r, v1i, k1r, k1i);
+  };
+
+  long long pos = 0, mask_pos = 0;
+  for (int p = 0; p < a.n_pieces; p++) {
+    const int n = a.piece_n[p];
+    const double h = a.piece_h[p];
+    const double h2 = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+    const int n_chunks = (n + kChunk - 1) / kChunk;
+    stage(0, pos, 2 * (n < kChunk ? n : kChunk) + 1);
+    for (int c = 0; c < n_chunks; c++) {
+      const int s0 = c * kChunk;
+      const int ns = (n - s0) < kChunk ? (n - s0) : kChunk;
+      if (c + 1 < n_chunks) {
+        const int s1 = s0 + kChunk;
+        stage((c + 1) & 1, pos + 2 * s1, 2 * ((n - s1) < kChunk ? (n - s1) : kChunk) + 1);
+        asm volatile("cp.async.wait_group 1;");
+      } else {
+        asm volatile("cp.async.wait_group 0;");
+      }
+      __syncthreads();
+      const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
+      const unsigned fast = __ldg(a.fast_mask + mask_pos + c);
+      for (int s = 0; s < ns; s++) {
+        if ((fast >> s) & 1u) {
+          const double* ent = tab + 2 * s * Ent::W;
+          Ent E;
+          double k0r[D], k0i[D], k1r[D], k1i[D], a0r[D], a0i[D], a1r[D], a1i[D], t0r[D], t0i[D], t1r[D], t1i[D];
+          E.load(ent);
+          double z0 = env0.re * E.c[0] - env0.im * E.s[0], z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          matvec2(E, y0r, y0i, y1r, y1i, k0r, k0i, k1r, k1i);
+          double c0 = h2 * z0, g0 = h6 * z0, c1 = h2 * z1, g1 = h6 * z1;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            t0r[i] = fma(c0, k0r[i], y0r[i]);
+            t0i[i] = fma(c0, k0i[i], y0i[i]);
+            a0r[i] = fma(g0, k0r[i], y0r[i]);
+            a0i[i] = fma(g0, k0i[i], y0i[i]);
+            t1r[i] = fma(c1, k1r[i], y1r[i]);
+            t1i[i] = fma(c1, k1i[i], y1i[i]);
+            a1r[i] = fma(g1, k1r[i], y1r[i]);
+            a1i[i] = fma(g1, k1i[i], y1i[i]);
+          }
+          E.load(ent + Ent::W);
+          z0 = env0.re * E.c[0] - env0.im * E.s[0];
+          z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
+          c0 = h2 * z0;
+          g0 = h3 * z0;
+          c1 = h2 * z1;
+          g1 = h3 * z1;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            t0r[i] = fma(c0, k0r[i], y0r[i]);
+            t0i[i] = fma(c0, k0i[i], y0i[i]);
+            a0r[i] = fma(g0, k0r[i], a0r[i]);
+            a0i[i] = fma(g0, k0i[i], a0i[i]);
+            t1r[i] = fma(c1, k1r[i], y1r[i]);
+            t1i[i] = fma(c1, k1i[i], y1i[i]);
+            a1r[i] = fma(g1, k1r[i], a1r[i]);
+            a1i[i] = fma(g1, k1i[i], a1i[i]);
+          }
+          matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
+          c0 = h * z0;
+          c1 = h * z1;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            t0r[i] = fma(c0, k0r[i], y0r[i]);
+            t0i[i] = fma(c0, k0i[i], y0i[i]);
+            a0r[i] = fma(g0, k0r[i], a0r[i]);
+            a0i[i] = fma(g0, k0i[i], a0i[i]);
+            t1r[i] = fma(c1, k1r[i], y1r[i]);
+            t1i[i] = fma(c1, k1i[i], y1i[i]);
+            a1r[i] = fma(g1, k1r[i], a1r[i]);
+            a1i[i] = fma(g1, k1i[i], a1i[i]);
+          }
+          E.load(ent + 2 * Ent::W);
+          z0 = env0.re * E.c[0] - env0.im * E.s[0];
+          z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
+          g0 = h6 * z0;
+          g1 = h6 * z1;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            y0r[i] = fma(g0, k0r[i], a0r[i]);
+            y0i[i] = fma(g0, k0i[i], a0i[i]);
+            y1r[i] = fma(g1, k1r[i], a1r[i]);
+            y1i[i] = fma(g1, k1i[i], a1i[i]);
+          }
+        } else {
+          const long long gp = pos + 2 * (s0 + s);
+          const int ia = __ldg(a.idx + gp), ib = __ldg(a.idx + gp + 1), ic = __ldg(a.idx + gp + 2);
+          SlowState<D, 1> st;
+          // trajectory 0
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            st.yr[i] = y0r[i];
+            st.yi[i] = y0i[i];
+          }
+          st.env[0] = env0;
+          st.cur_idx = cur_idx;
+          small_step_slow<D, 1, false, false, TRI>(a.self_dev, b0, gp, ia, ib, ic, h, &st);
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            y0r[i] = st.yr[i];
+            y0i[i] = st.yi[i];
+          }
+          env0 = st.env[0];
+          // trajectory 1
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            st.yr[i] = y1r[i];
+            st.yi[i] = y1i[i];
+          }
+          st.env[0] = env1;
+          st.cur_idx = cur_idx;
+          small_step_slow<D, 1, false, false, TRI>(a.self_dev, b1, gp, ia, ib, ic, h, &st);
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            y1r[i] = st.yr[i];
+            y1i[i] = st.yi[i];
+          }
+          env1 = st.env[0];
+          cur_idx = st.cur_idx;
+        }
+      }
+      __syncthreads();
+    }
+    pos += 2LL * n + 1;
+    mask_pos += n_chunks;
+    if (a.keep[p + 1]) emit();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage table: one thread per time point.  Layout per point (doubles), matching Entry<>::load:
 //   [KA x (cos, sin)(2 pi nu_k t)] [HAS_S: NE x ph_e*S_e] [KA x NE x (ph_e*T_ke [, ph_e*N_ke])]
 struct TableArgs {
@@ -675,7 +887,32 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
   if ((rc = m->work3.ensure(sizeof(SmallArgs)))) return rc;
   a.self_dev = (const SmallArgs*)m->work3.p;
   CASQ_CUDA(cudaMemcpyAsync(m->work3.p, &a, sizeof(SmallArgs), cudaMemcpyHostToDevice, st));
-  cudaError_t e = dispatch_small(d, KA, m->rwa, has_s, tri, a, st);
+  cudaError_t e;
+  int per_thread = (KA == 1 && !m->rwa && !has_s && B >= 16384) ? 2 : 1;
+  if (const char* env = getenv("CASQ_SMALL_TRAJ_PER_THREAD")) per_thread = atoi(env) == 2 && KA == 1 && !m->rwa && !has_s ? 2 : 1;
+  if (per_thread == 2) {
+    const int block = 64;
+    const long long threads = (B + 1) / 2;
+    const unsigned grid = (unsigned)((threads + block - 1) / block);
+    constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
+#define LAUNCH2(D_, T_)                                                                                                    \
+  {                                                                                                                        \
+    const size_t smem2 = 2 * (size_t)kEnt * Entry<D_, 1, false, false, T_>::W * sizeof(double);                            \
+    e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);       \
+    if (e == cudaSuccess) {                                                                                                \
+      sv_rk4_small2_kernel<D_, T_><<<grid, block, smem2, st>>>(a);                                                         \
+      e = cudaGetLastError();                                                                                              \
+    }                                                                                                                      \
+  }
+    if (d == 2) LAUNCH2(2, true)
+    else if (d == 3 && tri) LAUNCH2(3, true)
+    else if (d == 3) LAUNCH2(3, false)
+    else if (tri) LAUNCH2(4, true)
+    else LAUNCH2(4, false)
+#undef LAUNCH2
+  } else {
+    e = dispatch_small(d, KA, m->rwa, has_s, tri, a, st);
+  }
   if (e != cudaSuccess) CASQ_FAIL(CASQ_ERR_CUDA, "sv_rk4_small launch failed: %s", cudaGetErrorString(e));
   return CASQ_OK;
 }
