@@ -348,7 +348,10 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
   if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
   const int nt32 = (d + 31) / 32;
-  const dim3 grid_spmm((unsigned)((d + 7) / 8), (unsigned)B), grid_comb((unsigned)(nt32 * nt32), (unsigned)B);
+  int rpb = 8;  // 27 (one qutrit-triple block, more L1 reuse) measured no faster: 899 vs 875 ms
+  if (const char* env = getenv("CASQ_LB_RPB")) rpb = std::max(1, atoi(env));
+  a.rows_per_block = rpb;
+  const dim3 grid_spmm((unsigned)((d + rpb - 1) / rpb), (unsigned)B), grid_comb((unsigned)(nt32 * nt32), (unsigned)B);
   int nch = d <= 32 ? 1 : (d <= 64 ? 2 : 4);  // 4 chunks x 2 passes beats 8 x 1 at d = 243: registers buy occupancy, the kernel is latency bound
   if (const char* env = getenv("CASQ_LB_NCH")) nch = atoi(env);  // tuning knob: column chunks of 32 held in registers per pass
 

@@ -40,6 +40,7 @@ struct LbArgs {
   const int* idx;         // [NT] sample index
   const double* params;
   DevSlots slots;
+  int rows_per_block;     // SpMM: consecutive rows walked by one block
   const double2* cdense;  // [d*d] constant coefficient of the two-sided terms that gather rho[r,c] itself (x 1/2), or NULL
 };
 
@@ -134,7 +135,6 @@ __global__ void __launch_bounds__(256) lindblad_spmm_kernel(const LbArgs a, cons
   __shared__ int s_gs[LB_MAXQ + 1], s_goff[LB_MAXQ], s_gp[4 * LB_MAXQ];
   const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long b = blockIdx.y;
-  const int r = blockIdx.x * 8 + warp;
   if (threadIdx.x <= a.NG) s_gs[threadIdx.x] = a.grp_start[threadIdx.x];
   if (threadIdx.x < 2 * a.NP) s_gp[threadIdx.x] = a.grp_pairs[threadIdx.x];
   if (threadIdx.x < a.NG) {
@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(256) lindblad_spmm_kernel(const LbArgs a, cons
     s_goff[threadIdx.x] = a.u_delta[a.grp_pairs[2 * p0]] * d + a.u_delta[a.grp_pairs[2 * p0 + 1]];
   }
   __syncthreads();
-  if (r >= d) return;
+  // A block walks `rows_per_block` consecutive rows (27 = one block of the three lowest sites for qutrits): most source
+  // rows r + delta of its gathers then belong to the same block and are served by L1 instead of L2.
+  const int r_end = min(d, (int)(blockIdx.x + 1) * a.rows_per_block);
+  for (int r = blockIdx.x * a.rows_per_block + warp; r < r_end; r += 8) {
+  __syncwarp();
   const long long rowid = ((long long)set * a.B + b) * d + r;
   const double2* gu = cu + ((long long)set * a.B + b) * a.NU * d;
   const int cnt = L.lcnt[rowid], gc = L.gcnt[rowid];
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(256) lindblad_spmm_kernel(const LbArgs a, cons
     for (int ch = 0; ch < NCH; ch++)
       if (c0 + ch * 32 + lane < d) orow[c0 + ch * 32 + lane] = make_double2(ax[ch], ay[ch]);
   }
+}  // rows of this block
 }
 
 // ---------------------------------------------------------------------------------------------------------------
