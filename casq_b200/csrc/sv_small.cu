@@ -436,6 +436,12 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
   }
 }
 
+// Out-of-line envelope refresh for two trajectories (boundary steps of sv_rk4_small2_kernel).
+__device__ __noinline__ void small_env_refresh2(const SmallArgs* __restrict__ ap, long long b0, long long b1, int gidx, dcplx* out) {
+  casq_channel_envelopes<1>(ap->slots, ap->params, ap->B, b0, gidx, out);
+  casq_channel_envelopes<1>(ap->slots, ap->params, ap->B, b1, gidx, out + 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Two trajectories per thread for the headline shape (one channel, nothing static in the frame): the two
 // RK4 chains are independent, so every stage offers twice the instruction-level parallelism to the fp64 pipe
@@ -538,12 +544,44 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
       const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
       const unsigned fast = __ldg(a.fast_mask + mask_pos + c);
       for (int s = 0; s < ns; s++) {
-        if ((fast >> s) & 1u) {
+        // envelope values seen by stage 1 / stages 2,3 / stage 4: all equal to the cached one except on the ~1 step in
+        // 40 that touches a sample boundary, where an out-of-line refresh supplies the new sample
+        dcplx eA0 = env0, eB0 = env0, eC0 = env0, eA1 = env1, eB1 = env1, eC1 = env1;
+        if (!((fast >> s) & 1u)) {
+          const long long gp = pos + 2 * (s0 + s);
+          const int ia = __ldg(a.idx + gp), ib = __ldg(a.idx + gp + 1), ic = __ldg(a.idx + gp + 2);
+          dcplx fresh[2];
+          if (ia != cur_idx) {
+            cur_idx = ia;
+            small_env_refresh2(a.self_dev, b0, b1, ia, fresh);
+            env0 = fresh[0];
+            env1 = fresh[1];
+          }
+          eA0 = env0;
+          eA1 = env1;
+          if (ib != cur_idx) {
+            cur_idx = ib;
+            small_env_refresh2(a.self_dev, b0, b1, ib, fresh);
+            env0 = fresh[0];
+            env1 = fresh[1];
+          }
+          eB0 = env0;
+          eB1 = env1;
+          if (ic != cur_idx) {
+            cur_idx = ic;
+            small_env_refresh2(a.self_dev, b0, b1, ic, fresh);
+            env0 = fresh[0];
+            env1 = fresh[1];
+          }
+          eC0 = env0;
+          eC1 = env1;
+        }
+        {
           const double* ent = tab + 2 * s * Ent::W;
           Ent E;
           double k0r[D], k0i[D], k1r[D], k1i[D], a0r[D], a0i[D], a1r[D], a1i[D], t0r[D], t0i[D], t1r[D], t1i[D];
           E.load(ent);
-          double z0 = env0.re * E.c[0] - env0.im * E.s[0], z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          double z0 = eA0.re * E.c[0] - eA0.im * E.s[0], z1 = eA1.re * E.c[0] - eA1.im * E.s[0];
           matvec2(E, y0r, y0i, y1r, y1i, k0r, k0i, k1r, k1i);
           double c0 = h2 * z0, g0 = h6 * z0, c1 = h2 * z1, g1 = h6 * z1;
 #pragma unroll
@@ -558,8 +596,8 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
             a1i[i] = fma(g1, k1i[i], y1i[i]);
           }
           E.load(ent + Ent::W);
-          z0 = env0.re * E.c[0] - env0.im * E.s[0];
-          z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          z0 = eB0.re * E.c[0] - eB0.im * E.s[0];
+          z1 = eB1.re * E.c[0] - eB1.im * E.s[0];
           matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
           c0 = h2 * z0;
           g0 = h3 * z0;
@@ -591,8 +629,8 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
             a1i[i] = fma(g1, k1i[i], a1i[i]);
           }
           E.load(ent + 2 * Ent::W);
-          z0 = env0.re * E.c[0] - env0.im * E.s[0];
-          z1 = env1.re * E.c[0] - env1.im * E.s[0];
+          z0 = eC0.re * E.c[0] - eC0.im * E.s[0];
+          z1 = eC1.re * E.c[0] - eC1.im * E.s[0];
           matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
           g0 = h6 * z0;
           g1 = h6 * z1;
@@ -603,41 +641,6 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
             y1r[i] = fma(g1, k1r[i], a1r[i]);
             y1i[i] = fma(g1, k1i[i], a1i[i]);
           }
-        } else {
-          const long long gp = pos + 2 * (s0 + s);
-          const int ia = __ldg(a.idx + gp), ib = __ldg(a.idx + gp + 1), ic = __ldg(a.idx + gp + 2);
-          SlowState<D, 1> st;
-          // trajectory 0
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            st.yr[i] = y0r[i];
-            st.yi[i] = y0i[i];
-          }
-          st.env[0] = env0;
-          st.cur_idx = cur_idx;
-          small_step_slow<D, 1, false, false, TRI>(a.self_dev, b0, gp, ia, ib, ic, h, &st);
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            y0r[i] = st.yr[i];
-            y0i[i] = st.yi[i];
-          }
-          env0 = st.env[0];
-          // trajectory 1
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            st.yr[i] = y1r[i];
-            st.yi[i] = y1i[i];
-          }
-          st.env[0] = env1;
-          st.cur_idx = cur_idx;
-          small_step_slow<D, 1, false, false, TRI>(a.self_dev, b1, gp, ia, ib, ic, h, &st);
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            y1r[i] = st.yr[i];
-            y1i[i] = st.yi[i];
-          }
-          env1 = st.env[0];
-          cur_idx = st.cur_idx;
         }
       }
       __syncthreads();
