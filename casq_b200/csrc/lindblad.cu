@@ -20,14 +20,15 @@
 //     are table look-ups.  One class = one gathered rho element per side.
 //   * two-sided part: L_j rho L_j^+ [r,c] = sum over class pairs (q1,q2) of L_j of u_q1(r) conj(u_q2(c))
 //     rho[r+delta1, c+delta2].
-// Per RK4 stage: a row-wise SpMM kernel (Lm = A rho) and a combine kernel (Lm + Lm^+ + two-sided terms + fused RK4
-// combination with four rolling buffers); per step one coefficient kernel.  See lindblad_kernels.cuh.
+// Per RK4 stage ONE fused kernel on 64x64 tile pairs (k = M + M^+ with M = A rho + two-sided terms, plus the RK4
+// combination with four rolling buffers, lindblad_stage.cuh); per step one coefficient kernel (lindblad_kernels.cuh).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 
 #include "lindblad_kernels.cuh"
+#include "lindblad_stage.cuh"
 
 __global__ void sv_general_table_kernel(const double* __restrict__ times, long long NT, int KA, int d, int W,
                                         const double* __restrict__ two_pi_nu, const double* __restrict__ fe,
@@ -261,6 +262,18 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
   const size_t o_ph = off; off = align16(off + (size_t)d * 16);
   const size_t o_cd = off; off = align16(off + (cdense.empty() ? 16 : (size_t)d * d * 16));
+  const int ntile = (d + LB_TILE - 1) / LB_TILE;
+  std::vector<int> pair_ij;
+  for (int I = 0; I < ntile; I++)  // off-diagonal pairs (twice the work) first
+    for (int J = I + 1; J < ntile; J++) {
+      pair_ij.push_back(I);
+      pair_ij.push_back(J);
+    }
+  for (int I = 0; I < ntile; I++) {
+    pair_ij.push_back(I);
+    pair_ij.push_back(I);
+  }
+  const size_t o_pij = off; off = align16(off + pair_ij.size() * sizeof(int));
   std::vector<unsigned char> blob(off, 0);
   memcpy(&blob[o_qdelta], os.delta.data(), NQ * sizeof(int));
   memcpy(&blob[o_qcode], os.code.data(), (size_t)NQ * d * sizeof(short));
@@ -278,6 +291,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   }
   memcpy(&blob[o_V], m->V.data(), (size_t)d * d * 16);
   if (!cdense.empty()) memcpy(&blob[o_cd], cdense.data(), (size_t)d * d * 16);
+  memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
 
   const size_t n_per = (size_t)d * d;
   if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
@@ -286,7 +300,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
   if ((rc = m->work1.ensure(blob.size()))) return rc;
   if (NQ > LB_MAXQ) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "more than %d one-sided shift classes (%d): operators too dense for the structured path", LB_MAXQ, NQ);
-  if ((rc = m->work2.ensure(5 * (size_t)B * n_per * 16))) return rc;
+  if ((rc = m->work2.ensure(4 * (size_t)B * n_per * 16))) return rc;
   const size_t n_cq = (size_t)B * NQ * d, n_cu = (size_t)B * std::max(NU, 1) * d;
   if ((rc = m->work3.ensure(3 * (n_cq + n_cu) * 16))) return rc;
   double2* cq_all = (double2*)m->work3.p;
@@ -316,8 +330,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     CASQ_CUDA(cudaGetLastError());
   }
   unsigned char* dev = (unsigned char*)m->work1.p;
-  double2* bufs[5];  // y, y1, y2, y3, Lm
-  for (int i = 0; i < 5; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_per;
+  double2* bufs[4];  // y, y1, y2, y3
+  for (int i = 0; i < 4; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_per;
   {
     const long long n = (long long)B * n_per;
     lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)n_per, B, (const double2*)rho0_dev, rho0_batched, bufs[0]);
@@ -342,18 +356,15 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   a.params = params_dev;
   a.slots = ds;
   a.cdense = cdense.empty() ? nullptr : (const double2*)(dev + o_cd);
+  a.pair_ij = (const int*)(dev + o_pij);
   if (NU > LB_MAXQ || NG > LB_MAXQ || 2 * NP > 4 * LB_MAXQ)
     CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "too many two-sided classes for the structured Lindblad kernel (%d classes, %d pairs)", NU, NP);
   const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
   if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
-  const int nt32 = (d + 31) / 32;
-  int rpb = 8;  // 27 (one qutrit-triple block, more L1 reuse) measured no faster: 899 vs 875 ms
-  if (const char* env = getenv("CASQ_LB_RPB")) rpb = std::max(1, atoi(env));
-  a.rows_per_block = rpb;
-  const dim3 grid_spmm((unsigned)((d + rpb - 1) / rpb), (unsigned)B), grid_comb((unsigned)(nt32 * nt32), (unsigned)B);
-  int nch = d <= 32 ? 1 : (d <= 64 ? 2 : 4);  // 4 chunks x 2 passes beats 8 x 1 at d = 243: registers buy occupancy, the kernel is latency bound
-  if (const char* env = getenv("CASQ_LB_NCH")) nch = atoi(env);  // tuning knob: column chunks of 32 held in registers per pass
+  const dim3 grid_pairs((unsigned)(pair_ij.size() / 2), (unsigned)B);
+  const size_t smem_stage = lindblad_stage_smem(NQ, NU, NG);
+  CASQ_CUDA(cudaFuncSetAttribute(lindblad_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
 
   std::vector<cplx> ph(d);
   int t_slot = 0;
@@ -388,20 +399,13 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
         const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
         LbStage sg;
         sg.in = bufs[stage - 1];
-        sg.lm = bufs[4];
         sg.y = bufs[0];
         sg.y1 = bufs[1];
         sg.y2 = bufs[2];
         sg.out = stage == 4 ? bufs[0] : bufs[stage];
         sg.stage = stage;
         sg.h = h_piece;
-        switch (nch) {
-          case 1: lindblad_spmm_kernel<1><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
-          case 2: lindblad_spmm_kernel<2><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
-          case 4: lindblad_spmm_kernel<4><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
-          default: lindblad_spmm_kernel<8><<<grid_spmm, 256, 0, st>>>(a, lists, cu_all, set, sg.in, bufs[4]); break;
-        }
-        lindblad_combine_kernel<<<grid_comb, dim3(32, 8), 0, st>>>(d, sg);
+        lindblad_stage_kernel<<<grid_pairs, 512, smem_stage, st>>>(a, lists, cu_all, set, sg);
       }
       pos += 2;
     }

@@ -6,15 +6,13 @@
 //
 //   lindblad_coef_kernel     once per step: per trajectory and stage time, the class coefficient vectors and, per
 //                            row, the COMPACTED list of (coefficient, source-row offset) of the classes acting on it.
-//   lindblad_spmm_kernel     Lm = A rho as a row-wise SpMM: one warp owns a full output row, lanes own columns
-//                            (8 x 32 column chunks in registers), so each (coefficient, offset) pair is loaded once
-//                            per row and amortised over 243 elements: the inner loop is LDG.128 + 4 DFMA.
-//   lindblad_combine_kernel  k = Lm + Lm^+ (transposed tile through shared memory) + two-sided gathers, then the
-//                            fused RK4 combination with four rolling buffers.
+//   lindblad_stage_kernel    (lindblad_stage.cuh) one launch per RK4 stage: k = M + M^+ on 64x64 tile pairs, fused
+//                            with the RK4 combination.
 //
-// Round-1 history (profiles/r01_ncu_lindblad_*.txt): tile-pair kernels that gathered per 27x27 tile spent
-// >90 % of their instructions on per-tile set-up and index arithmetic (1 500 thread-instructions per element
-// pair against ~100 useful DFMA) and ran at the same 75-85 traj/s whatever the gather count or block shape.
+// Round-1 history (profiles/r01_ncu_lindblad_*.txt): (1) tile-pair kernels that gathered per 27x27 tile spent >90 %
+// of their instructions on per-tile set-up and index arithmetic and ran at 75-85 traj/s whatever the block shape;
+// (2) a row-wise SpMM (M = A rho, one warp per row) followed by a transposing combine kernel reached 145 traj/s with
+// 27 matrix passes through HBM per step; (3) the fused stage kernel replaced both (156 traj/s, ~11 passes).
 #pragma once
 #include "common.cuh"
 #include "envelope.cuh"
@@ -40,7 +38,7 @@ struct LbArgs {
   const int* idx;         // [NT] sample index
   const double* params;
   DevSlots slots;
-  int rows_per_block;     // SpMM: consecutive rows walked by one block
+  const int* pair_ij;      // [NT(NT+1)/2][2] tile pairs (I <= J) of the fused stage kernel
   const double2* cdense;  // [d*d] constant coefficient of the two-sided terms that gather rho[r,c] itself (x 1/2), or NULL
 };
 
@@ -122,118 +120,10 @@ __global__ void __launch_bounds__(256) lindblad_coef_kernel(const LbArgs a, long
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// M = A rho + 1/2 sum_j L_j rho L_j^+   (so that k = M + M^+: the two-sided part is Hermitian by itself).
-// grid (ceil(d/8), B), 8 warps per block, one output row per warp; NCH = column chunks of 32 per pass.
-template <int NCH>
-__global__ void __launch_bounds__(256) lindblad_spmm_kernel(const LbArgs a, const LbLists L, const double2* __restrict__ cu, int set,
-                                                            const double2* __restrict__ in_all, double2* __restrict__ m_all) {
-  __shared__ double2 s_c[8][LB_MAXQ];
-  __shared__ int s_o[8][LB_MAXQ];
-  __shared__ double2 s_ul[8][LB_MAXQ];  // 1/2 * row factors of the two-sided classes
-  __shared__ int s_g[8][LB_MAXQ];       // gather groups acting on the row
-  __shared__ int s_gs[LB_MAXQ + 1], s_goff[LB_MAXQ], s_gp[4 * LB_MAXQ];
-  const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long b = blockIdx.y;
-  if (threadIdx.x <= a.NG) s_gs[threadIdx.x] = a.grp_start[threadIdx.x];
-  if (threadIdx.x < 2 * a.NP) s_gp[threadIdx.x] = a.grp_pairs[threadIdx.x];
-  if (threadIdx.x < a.NG) {
-    const int p0 = a.grp_start[threadIdx.x];
-    s_goff[threadIdx.x] = a.u_delta[a.grp_pairs[2 * p0]] * d + a.u_delta[a.grp_pairs[2 * p0 + 1]];
-  }
-  __syncthreads();
-  // A block walks `rows_per_block` consecutive rows (27 = one block of the three lowest sites for qutrits): most source
-  // rows r + delta of its gathers then belong to the same block and are served by L1 instead of L2.
-  const int r_end = min(d, (int)(blockIdx.x + 1) * a.rows_per_block);
-  for (int r = blockIdx.x * a.rows_per_block + warp; r < r_end; r += 8) {
-  __syncwarp();
-  const long long rowid = ((long long)set * a.B + b) * d + r;
-  const double2* gu = cu + ((long long)set * a.B + b) * a.NU * d;
-  const int cnt = L.lcnt[rowid], gc = L.gcnt[rowid];
-  if (lane < cnt) {
-    s_c[warp][lane] = L.lcoef[rowid * a.NQ + lane];
-    s_o[warp][lane] = L.loff[rowid * a.NQ + lane];
-  }
-  if (lane < gc) s_g[warp][lane] = L.glist[rowid * a.NG + lane];
-  if (lane < a.NU) {
-    const double2 u = gu[lane * d + r];
-    s_ul[warp][lane] = make_double2(0.5 * u.x, 0.5 * u.y);
-  }
-  __syncwarp();
-  const double2* prow = in_all + b * (long long)d * d + (long long)r * d;
-  double2* orow = m_all + b * (long long)d * d + (long long)r * d;
-  for (int c0 = 0; c0 < d; c0 += 32 * NCH) {
-    double ax[NCH], ay[NCH];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ch++) ax[ch] = ay[ch] = 0.0;
-    for (int k = 0; k < cnt; k++) {
-      const double2 cf = s_c[warp][k];
-      const double2* src = prow + s_o[warp][k] + c0 + lane;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        if (c0 + ch * 32 + lane < d) {
-          const double2 v = __ldg(src + ch * 32);
-          ax[ch] = fma(cf.x, v.x, fma(-cf.y, v.y, ax[ch]));
-          ay[ch] = fma(cf.x, v.y, fma(cf.y, v.x, ay[ch]));
-        }
-      }
-    }
-    if (a.cdense) {
-      const double2* cd = a.cdense + (long long)r * d + c0 + lane;
-      const double2* src = prow + c0 + lane;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        if (c0 + ch * 32 + lane < d) {
-          const double2 cf = __ldg(cd + ch * 32);
-          const double2 v = __ldg(src + ch * 32);
-          ax[ch] = fma(cf.x, v.x, fma(-cf.y, v.y, ax[ch]));
-          ay[ch] = fma(cf.x, v.y, fma(cf.y, v.x, ay[ch]));
-        }
-      }
-    }
-    for (int k = 0; k < gc; k++) {
-      const int g = s_g[warp][k];
-      const double2* src = prow + s_goff[g] + c0 + lane;
-      const int p0 = s_gs[g], p1 = s_gs[g + 1];
-      // pair loop outside, chunks unrolled inside: NCH independent loads in flight per instruction group
-      double cx[NCH], cy[NCH];
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) cx[ch] = cy[ch] = 0.0;
-      for (int p = p0; p < p1; p++) {
-        const double2 ul = s_ul[warp][s_gp[2 * p]];
-        const double2* urp = gu + s_gp[2 * p + 1] * d + c0 + lane;
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch++) {
-          if (c0 + ch * 32 + lane < d) {
-            const double2 ur = __ldg(urp + ch * 32);  // conj(ur) below
-            cx[ch] = fma(ul.x, ur.x, fma(ul.y, ur.y, cx[ch]));
-            cy[ch] = fma(ul.y, ur.x, fma(-ul.x, ur.y, cy[ch]));
-          }
-        }
-      }
-#pragma unroll
-      for (int ch = 0; ch < NCH; ch++) {
-        // a non-zero coefficient implies the shifted indices are valid
-        if (c0 + ch * 32 + lane < d && (cx[ch] != 0.0 || cy[ch] != 0.0)) {
-          const double2 v = __ldg(src + ch * 32);
-          ax[ch] = fma(cx[ch], v.x, fma(-cy[ch], v.y, ax[ch]));
-          ay[ch] = fma(cx[ch], v.y, fma(cy[ch], v.x, ay[ch]));
-        }
-      }
-    }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ch++)
-      if (c0 + ch * 32 + lane < d) orow[c0 + ch * 32 + lane] = make_double2(ax[ch], ay[ch]);
-  }
-}  // rows of this block
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// k = M + M^+ and the RK4 combination.  grid (nt32*nt32, B), block (32, 8): a 32x32 tile, 4 rows per thread,
-// lane = column; the partner tile (J,I) is transposed through shared memory.
+// One RK4 stage of the fused kernel (lindblad_stage.cuh): four rolling buffers y, y1, y2, y3 and no accumulator:
+//   y1 = y + h/2 k(y), y2 = y + h/2 k(y1), y3 = y + h k(y2), y <- (y1 + 2 y2 + y3 - y)/3 + h/6 k(y3).
 struct LbStage {
-  const double2* in;   // stage input (rho at this stage)
-  const double2* lm;   // M of this stage
+  const double2* in;   // stage input (rho at this stage): the gather source
   const double2* y;    // step start
   const double2* y1;
   const double2* y2;
@@ -241,45 +131,6 @@ struct LbStage {
   int stage;  // 1..4
   double h;
 };
-
-__global__ void __launch_bounds__(256) lindblad_combine_kernel(int d, const LbStage s) {
-  __shared__ double2 s_T[32][33];
-  const int nt = (d + 31) / 32;
-  const int I = blockIdx.x / nt, J = blockIdx.x - I * nt;
-  const long long base = (long long)blockIdx.y * d * d;
-  const int rI = I * 32, rJ = J * 32;
-  const int lane = threadIdx.x, ty = threadIdx.y;
-  const double2* lm = s.lm + base;
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const int jl = ty + 8 * u;
-    if (rJ + jl < d && rI + lane < d) s_T[jl][lane] = lm[(long long)(rJ + jl) * d + rI + lane];
-  }
-  __syncthreads();
-  const int c = rJ + lane;
-  if (c >= d) return;
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const int rl = ty + 8 * u, r = rI + rl;
-    if (r >= d) continue;
-    const long long o = (long long)r * d + c;
-    const double2 l1 = lm[o];
-    const double2 lt = s_T[lane][rl];
-    const double2 y0 = s.y[base + o];
-    const double kx = l1.x + lt.x, ky = l1.y - lt.y;
-    double2 res;
-    if (s.stage == 1 || s.stage == 2) {
-      res = make_double2(fma(0.5 * s.h, kx, y0.x), fma(0.5 * s.h, ky, y0.y));
-    } else if (s.stage == 3) {
-      res = make_double2(fma(s.h, kx, y0.x), fma(s.h, ky, y0.y));
-    } else {
-      const double2 v1 = s.y1[base + o], v2 = s.y2[base + o], v3 = s.in[base + o];
-      const double t3 = 1.0 / 3.0, h6 = s.h * (1.0 / 6.0);
-      res = make_double2(fma(h6, kx, t3 * (v1.x + 2.0 * v2.x + v3.x - y0.x)), fma(h6, ky, t3 * (v1.y + 2.0 * v2.y + v3.y - y0.y)));
-    }
-    s.out[base + o] = res;
-  }
-}
 
 // rho0 broadcast / copy into the working buffer
 __global__ void lindblad_init_kernel(long long n_per, long long B, const double2* __restrict__ rho0, int batched,
