@@ -134,20 +134,87 @@ __device__ void wsolve(int d_, int lane, double2* Q, double2* Pm) {
   }
 }
 
+// d = 9: the augmented matrix [Q | P] (9 x 18) lives in REGISTERS, lane = (row i, block of 6 columns), 27 lanes.
+// Rows are never swapped: the pivot of column k is the largest entry among the rows not used as a pivot yet (partial
+// pivoting up to a row permutation) and row i is written to row "variable it solved" of the result at the end.  The
+// arg-max is ONE redux.sync on a 32-bit key (upper bits of |x|^2, row index in the low 4 bits: candidates that agree to
+// 2^-16 are interchangeable as pivots).  Per pivot: 1 REDUX + 4 SHFL + the pivot row through shared memory, against the
+// generic version's five shuffle rounds, physical row swaps and 162 element updates strided over 32 lanes.
+__device__ __forceinline__ void wsolve9(int lane, double2* Q, double2* Pm) {
+  const int i = lane / 3, jb = lane - 3 * i;
+  const bool act = lane < 27;
+  double2 v[6];
+#pragma unroll
+  for (int t = 0; t < 6; t++) {
+    const int c = 6 * jb + t;
+    v[t] = act ? (c < 9 ? Q[i * 9 + c] : Pm[i * 9 + c - 9]) : make_double2(0.0, 0.0);
+  }
+  __syncwarp();  // Q is scratch from here on
+  double2* s_row = Q;     // [18] scaled pivot row
+  double2* s_f = Q + 18;  // [9]  elimination factors (column k)
+  int myk = -1;           // the variable this lane's row solved, -1 while the row is still a pivot candidate
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const int kb = k / 6, kt = k % 6;
+    const double2 x = v[kt];
+    unsigned key = 0;
+    if (act && jb == kb && myk < 0) key = ((unsigned)__double2hiint(x.x * x.x + x.y * x.y) & 0xFFFFFFF0u) | (unsigned)(15 - i);
+    key = __reduce_max_sync(0xffffffffu, key);
+    const int pr = 15 - (int)(key & 15u);
+    const double px = __shfl_sync(0xffffffffu, x.x, 3 * pr + kb), py = __shfl_sync(0xffffffffu, x.y, 3 * pr + kb);
+    const double inv_n = 1.0 / (px * px + py * py);
+    const double2 pinv = make_double2(px * inv_n, -py * inv_n);
+    if (act) {
+      if (i == pr) {
+#pragma unroll
+        for (int t = 0; t < 6; t++) {
+          v[t] = cmul(v[t], pinv);
+          s_row[6 * jb + t] = v[t];
+        }
+        myk = k;
+      } else if (jb == kb) {
+        s_f[i] = x;
+      }
+    }
+    __syncwarp();
+    if (act && i != pr) {
+      const double2 f = s_f[i];
+#pragma unroll
+      for (int t = 0; t < 6; t++) {
+        const double2 p = s_row[6 * jb + t];
+        v[t].x = fma(-f.x, p.x, fma(f.y, p.y, v[t].x));
+        v[t].y = fma(-f.x, p.y, fma(-f.y, p.x, v[t].y));
+      }
+    }
+    __syncwarp();
+  }
+  if (act) {
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+      const int c = 6 * jb + t;
+      if (c >= 9) Pm[myk * 9 + c - 9] = v[t];
+    }
+  }
+  __syncwarp();
+}
+
 // E = expm(A).  Workspace: A2, A4, A6, Um, Vm, T1 (each d*d).  A is overwritten (scaled).
 template <int DT>
 __device__ void wexpm(int d_, int lane, double2* A, double2* E, double2* A2, double2* A4, double2* A6, double2* Um,
                       double2* Vm, double2* T1) {
   const int d = DT > 0 ? DT : d_;
   const int n2 = d * d;
-  // ||A||_1 = max column sum
+  // ||A||_1 = max column sum: element magnitudes spread over the warp (T1 as scratch), then one lane per column
+  for (int e = lane; e < n2; e += 32) T1[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
+  __syncwarp();
   double nrm = 0.0;
   for (int j = lane; j < d; j += 32) {
     double s = 0.0;
-    for (int i = 0; i < d; i++) s += hypot(A[i * d + j].x, A[i * d + j].y);
+    for (int i = 0; i < d; i++) s += T1[i * d + j].x;
     nrm = fmax(nrm, s);
   }
   for (int o = 16; o > 0; o >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
+  __syncwarp();
   int m, s = 0;
   if (nrm < 1.495585217958292e-2)
     m = 3;
@@ -231,7 +298,10 @@ __device__ void wexpm(int d_, int lane, double2* A, double2* E, double2* A2, dou
     E[e] = make_double2(Vm[e].x + Um[e].x, Vm[e].y + Um[e].y);
   }
   __syncwarp();
-  wsolve<DT>(d, lane, T1, E);
+  if (DT == 9)
+    wsolve9(lane, T1, E);
+  else
+    wsolve<DT>(d, lane, T1, E);
   for (int q = 0; q < s; q++) {
     wmatmul<DT>(d, lane, T1, E, E);
     for (int e = lane; e < n2; e += 32) E[e] = T1[e];
