@@ -198,19 +198,23 @@ __device__ __forceinline__ void wsolve9(int lane, double2* Q, double2* Pm) {
   __syncwarp();
 }
 
-// E = expm(A).  Workspace: A2, A4, A6, Um, Vm, T1 (each d*d).  A is overwritten (scaled).
+// expm(A) with FOUR work matrices X1..X4 (d*d each); A is overwritten (scaled); returns the buffer holding the result
+// (X1 or X2).  Orders 3/5/7/9 by Higham's theta_m; above theta_9 the matrix is scaled down to theta_9 and squared back.
+// (Higham switches to [13/13] with theta_13 there: same backward-error bound, but it needs three more live matrices.
+// With A, the running product and X1..X4 a warp needs 6 matrices of shared memory instead of 9, which is what lets all
+// 4 096 warps of BASELINE cfg 3 be resident at once.)  Buffer life: X1 = A^2 -> U -> P -> result; X2 = A^4 -> squaring
+// scratch; X3 = A^6 -> V -> Q; X4 = |A| scratch -> A^8 -> odd polynomial.
 template <int DT>
-__device__ void wexpm(int d_, int lane, double2* A, double2* E, double2* A2, double2* A4, double2* A6, double2* Um,
-                      double2* Vm, double2* T1) {
+__device__ double2* wexpm(int d_, int lane, double2* A, double2* X1, double2* X2, double2* X3, double2* X4) {
   const int d = DT > 0 ? DT : d_;
   const int n2 = d * d;
-  // ||A||_1 = max column sum: element magnitudes spread over the warp (T1 as scratch), then one lane per column
-  for (int e = lane; e < n2; e += 32) T1[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
+  // ||A||_1 = max column sum: element magnitudes spread over the warp (X4 as scratch), then one lane per column
+  for (int e = lane; e < n2; e += 32) X4[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
   __syncwarp();
   double nrm = 0.0;
   for (int j = lane; j < d; j += 32) {
     double s = 0.0;
-    for (int i = 0; i < d; i++) s += T1[i * d + j].x;
+    for (int i = 0; i < d; i++) s += X4[i * d + j].x;
     nrm = fmax(nrm, s);
   }
   for (int o = 16; o > 0; o >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
@@ -222,11 +226,9 @@ __device__ void wexpm(int d_, int lane, double2* A, double2* E, double2* A2, dou
     m = 5;
   else if (nrm < 9.504178996162932e-1)
     m = 7;
-  else if (nrm < 2.097847961257068e0)
-    m = 9;
   else {
-    m = 13;
-    const double r = nrm / 5.371920351148152e0;
+    m = 9;
+    const double r = nrm / 2.097847961257068e0;
     s = r > 1.0 ? (int)ceil(log2(r)) : 0;
     if (s > 0) {
       const double sc = ldexp(1.0, -s);
@@ -234,101 +236,79 @@ __device__ void wexpm(int d_, int lane, double2* A, double2* E, double2* A2, dou
       __syncwarp();
     }
   }
+  double2 *A2 = X1, *A4 = X2, *A6 = X3, *A8 = X4, *Od = X4, *Vm = X3;
   wmatmul<DT>(d, lane, A2, A, A);
   auto diag = [&](int e) { return (e / d) == (e % d) ? 1.0 : 0.0; };
   if (m == 3) {
     const double b[4] = {120., 60., 12., 1.};
     for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(b[3] * A2[e].x + b[1] * diag(e), b[3] * A2[e].y);
+      Od[e] = make_double2(b[3] * A2[e].x + b[1] * diag(e), b[3] * A2[e].y);
       Vm[e] = make_double2(b[2] * A2[e].x + b[0] * diag(e), b[2] * A2[e].y);
     }
   } else if (m == 5) {
     const double b[6] = {30240., 15120., 3360., 420., 30., 1.};
     wmatmul<DT>(d, lane, A4, A2, A2);
     for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[5] * A4[e].y + b[3] * A2[e].y);
+      Od[e] = make_double2(b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[5] * A4[e].y + b[3] * A2[e].y);
       Vm[e] = make_double2(b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e), b[4] * A4[e].y + b[2] * A2[e].y);
     }
   } else if (m == 7) {
     const double b[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
     wmatmul<DT>(d, lane, A4, A2, A2);
     wmatmul<DT>(d, lane, A6, A4, A2);
-    for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
-                           b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
-      Vm[e] = make_double2(b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
-                           b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
+    for (int e = lane; e < n2; e += 32) {  // V overwrites A^6 element by element
+      const double2 a6 = A6[e];
+      Od[e] = make_double2(b[7] * a6.x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[7] * a6.y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[6] * a6.x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e), b[6] * a6.y + b[4] * A4[e].y + b[2] * A2[e].y);
     }
-  } else if (m == 9) {
+  } else {
     const double b[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
     wmatmul<DT>(d, lane, A4, A2, A2);
     wmatmul<DT>(d, lane, A6, A4, A2);
-    wmatmul<DT>(d, lane, Um, A6, A2);  // A8 in Um (temporarily)
-    for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(b[9] * Um[e].x + b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
-                           b[9] * Um[e].y + b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
-      Vm[e] = make_double2(b[8] * Um[e].x + b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
-                           b[8] * Um[e].y + b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
-    }
-  } else {
-    const double b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
-                          10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.};
-    wmatmul<DT>(d, lane, A4, A2, A2);
-    wmatmul<DT>(d, lane, A6, A4, A2);
-    // W1 = b13 A6 + b11 A4 + b9 A2 ; Z1 = b12 A6 + b10 A4 + b8 A2  (in T1 / E)
-    for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(b[13] * A6[e].x + b[11] * A4[e].x + b[9] * A2[e].x, b[13] * A6[e].y + b[11] * A4[e].y + b[9] * A2[e].y);
-      E[e] = make_double2(b[12] * A6[e].x + b[10] * A4[e].x + b[8] * A2[e].x, b[12] * A6[e].y + b[10] * A4[e].y + b[8] * A2[e].y);
-    }
-    __syncwarp();
-    wmatmul<DT>(d, lane, Um, A6, T1);  // A6 W1
-    wmatmul<DT>(d, lane, Vm, A6, E);   // A6 Z1
-    for (int e = lane; e < n2; e += 32) {
-      T1[e] = make_double2(Um[e].x + b[7] * A6[e].x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
-                           Um[e].y + b[7] * A6[e].y + b[5] * A4[e].y + b[3] * A2[e].y);
-      Vm[e] = make_double2(Vm[e].x + b[6] * A6[e].x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
-                           Vm[e].y + b[6] * A6[e].y + b[4] * A4[e].y + b[2] * A2[e].y);
+    wmatmul<DT>(d, lane, A8, A6, A2);
+    for (int e = lane; e < n2; e += 32) {  // the polynomials overwrite A^8 and A^6 element by element
+      const double2 a8 = A8[e], a6 = A6[e];
+      Od[e] = make_double2(b[9] * a8.x + b[7] * a6.x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
+                           b[9] * a8.y + b[7] * a6.y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[8] * a8.x + b[6] * a6.x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
+                           b[8] * a8.y + b[6] * a6.y + b[4] * A4[e].y + b[2] * A2[e].y);
     }
   }
   __syncwarp();
-  wmatmul<DT>(d, lane, Um, A, T1);  // U = A * (odd polynomial part)
-  // Q = V - U (in T1), P = V + U (in E); solve Q R = P
+  double2* Um = X1;  // A^2 is dead
+  wmatmul<DT>(d, lane, Um, A, Od);  // U = A * (odd polynomial part)
+  // Q = V - U (over V), P = V + U (over U); solve Q R = P
   for (int e = lane; e < n2; e += 32) {
-    T1[e] = make_double2(Vm[e].x - Um[e].x, Vm[e].y - Um[e].y);
-    E[e] = make_double2(Vm[e].x + Um[e].x, Vm[e].y + Um[e].y);
+    const double2 v = Vm[e], u = Um[e];
+    X3[e] = make_double2(v.x - u.x, v.y - u.y);
+    X1[e] = make_double2(v.x + u.x, v.y + u.y);
   }
   __syncwarp();
   if (DT == 9)
-    wsolve9(lane, T1, E);
+    wsolve9(lane, X3, X1);
   else
-    wsolve<DT>(d, lane, T1, E);
+    wsolve<DT>(d, lane, X3, X1);
+  double2 *E = X1, *Sq = X2;
   for (int q = 0; q < s; q++) {
-    wmatmul<DT>(d, lane, T1, E, E);
-    for (int e = lane; e < n2; e += 32) E[e] = T1[e];
-    __syncwarp();
+    wmatmul<DT>(d, lane, Sq, E, E);
+    double2* t = E;
+    E = Sq;
+    Sq = t;
   }
+  return E;
 }
 
+#define PROP_NBUF 6  // A, running product, X1..X4
+
 template <int DT>
-__global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const PropArgs a) {
+__global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_expm_kernel(const PropArgs a) {
   const int d = DT > 0 ? DT : a.d, KA = a.KA, n2 = d * d;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* s_S = reinterpret_cast<double2*>(smem_raw);
-  double2* s_P = s_S + n2;
-  double2* s_N = s_P + (size_t)KA * n2;
-  double2* s_ws = s_N + (size_t)(a.rwa ? KA : 0) * n2;  // per-warp workspaces follow
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) s_S[i] = a.S[i];
-  for (int i = threadIdx.x; i < KA * n2; i += blockDim.x) {
-    s_P[i] = a.P[i];
-    if (a.rwa) s_N[i] = a.N[i];
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long b = (long long)blockIdx.x * PROP_WARPS + warp;
   if (b >= a.B) return;
-  double2* ws = s_ws + (size_t)warp * 9 * n2;
-  double2 *A = ws, *E = ws + n2, *Uacc = ws + 2 * n2, *A2 = ws + 3 * n2, *A4 = ws + 4 * n2, *A6 = ws + 5 * n2, *Um = ws + 6 * n2,
-          *Vm = ws + 7 * n2, *T1 = ws + 8 * n2;
+  double2* ws = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * PROP_NBUF * n2;
+  double2 *A = ws, *Uacc = ws + n2, *X1 = ws + 2 * n2, *X2 = ws + 3 * n2, *X3 = ws + 4 * n2, *X4 = ws + 5 * n2;
   for (int e = lane; e < n2; e += 32) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
   __syncwarp();
 
@@ -361,16 +341,17 @@ __global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const 
         }
       }
       const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
-      // A = h * (-i) * p_i conj(p_j) (S + sum_k z_k P_k + conj(z_k) N_k)
+      // A = h * (-i) * p_i conj(p_j) (S + sum_k z_k P_k + conj(z_k) N_k); the operators are read through L1 (they are
+      // the same 4 kB for every warp of the grid), shared memory is kept for the per-warp work matrices
       for (int e = lane; e < n2; e += 32) {
         const int i = e / d, j = e - i * d;
-        double2 m = s_S[e];
+        double2 m = __ldg(a.S + e);
 #pragma unroll
         for (int k = 0; k < PROP_MAXK; k++) {
           if (k < KA) {
-            const double2 P = s_P[(size_t)k * n2 + e];
+            const double2 P = __ldg(a.P + (size_t)k * n2 + e);
             if (a.rwa) {
-              const double2 N = s_N[(size_t)k * n2 + e];
+              const double2 N = __ldg(a.N + (size_t)k * n2 + e);
               m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
               m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
             } else {
@@ -385,10 +366,11 @@ __global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const 
         A[e] = make_double2(h * g.y, -h * g.x);  // -i g
       }
       __syncwarp();
-      wexpm<DT>(d, lane, A, E, A2, A4, A6, Um, Vm, T1);
-      wmatmul<DT>(d, lane, T1, E, Uacc);
-      for (int e = lane; e < n2; e += 32) Uacc[e] = T1[e];
-      __syncwarp();
+      double2* E = wexpm<DT>(d, lane, A, X1, X2, X3, X4);
+      wmatmul<DT>(d, lane, X4, E, Uacc);  // X4 is free once the odd polynomial has been consumed
+      double2* t = Uacc;
+      Uacc = X4;
+      X4 = t;
       pos += 2;
     }
     pos += 1;
@@ -398,11 +380,11 @@ __global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const 
   if (a.identityU) {
     for (int e = lane; e < n2; e += 32) o[e] = Uacc[e];
   } else {
-    for (int e = lane; e < n2; e += 32) {  // T1 = V U
+    for (int e = lane; e < n2; e += 32) {  // X1 = V U
       const int i = e / d, j = e - i * d;
       double2 acc = make_double2(0.0, 0.0);
       for (int k = 0; k < d; k++) acc = cfma(__ldg(a.U + i * d + k), Uacc[k * d + j], acc);
-      T1[e] = acc;
+      X1[e] = acc;
     }
     __syncwarp();
     for (int e = lane; e < n2; e += 32) {
@@ -410,7 +392,7 @@ __global__ void __launch_bounds__(32 * PROP_WARPS) propagator_expm_kernel(const 
       double2 acc = make_double2(0.0, 0.0);
       for (int k = 0; k < d; k++) {
         const double2 v = __ldg(a.U + j * d + k);
-        acc = cfma(T1[i * d + k], make_double2(v.x, -v.y), acc);
+        acc = cfma(X1[i * d + k], make_double2(v.x, -v.y), acc);
       }
       o[e] = acc;
     }
@@ -504,7 +486,7 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
   a.N = a.P + (size_t)KA * n2;
   a.U = a.N + (size_t)KA * n2;
   a.identityU = m->U_is_identity ? 1 : 0;
-  const size_t smem = ((size_t)(1 + KA * (m->rwa ? 2 : 1)) * n2 + (size_t)PROP_WARPS * 9 * n2) * sizeof(double2);
+  const size_t smem = (size_t)PROP_WARPS * PROP_NBUF * n2 * sizeof(double2);
   const unsigned grid = (unsigned)((B + PROP_WARPS - 1) / PROP_WARPS);
   // the dimensions transmon models produce get compile-time loop bounds (index arithmetic was 80 % of the generic kernel)
 #define PROP_LAUNCH(DT_)                                                                                              \
