@@ -32,9 +32,9 @@ struct Dopri5Args {
   double* out;        // [B][T_out][D] c128
   long long* nsteps;  // [B][2] attempted, accepted (may be NULL)
   int* status;        // [B] 0 ok, 1 mxstep hit, 2 dt underflow (may be NULL)
-  DevSlots slots;
+  const double2* env_tab;  // [KA][n_total][B] envelope samples of every trajectory (dp_env_table_kernel)
   int n_total;
-  double dt_sample;
+  double dt_sample, inv_dt_sample;
   double rtol, atol, hmax;
   long long mxstep;
   int rwa;
@@ -66,27 +66,78 @@ __device__ __forceinline__ int dev_sample_index(double t, double dt, int n_total
   return (int)fl;
 }
 
-template <int D, int KA>
-struct DpState {
-  int cur_idx;
+// The same index without the iterative fmod: a guess from one multiplication, corrected by the EXACT sign of the
+// remainder t - q dt (one FMA).  Only a remainder that rounds to exactly dt is ambiguous; that case (times that are
+// exact multiples of dt) takes the reference path above.
+__device__ __forceinline__ int dev_sample_index_fast(double t, double dt, double inv_dt, int n_total) {
+  double q = floor(t * inv_dt);
+  const double r = fma(-q, dt, t);
+  if (r == dt) return dev_sample_index(t, dt, n_total);
+  q += (r < 0.0) ? -1.0 : (r > dt ? 1.0 : 0.0);
+  q = fmin(fmax(q, -1.0), (double)n_total);
+  return (int)q;
+}
+
+// Branch-free fp64 sincos for |x| < 1e5 (phases reach ~2e3 rad here): two-FMA Cody-Waite reduction by pi/2 and the
+// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The library sincos hides a slow-path branch in every call,
+// which keeps the compiler from overlapping the carrier and Bohr-phase evaluations of a stage.
+__device__ __forceinline__ void dp_sincos(double x, double* sn, double* cs) {
+  if (fabs(x) >= 1.0e5) {
+    sincos(x, sn, cs);
+    return;
+  }
+  const double n = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-n, 1.5707963267948966, x);
+  r = fma(-n, 6.123233995736766e-17, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = (int)n;
+  const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// Envelope samples of every trajectory, evaluated once per solve: with per-thread stage times almost every RHS call
+// of a warp has SOME lane crossing a sample boundary, so the on-the-fly evaluation (2 exp, sincos, divisions) ran on
+// every call; a look-up in a [KA][n_total][B] table (neighbouring lanes sit in the same or adjacent samples: coalesced)
+// replaces it.
+template <int KA>
+__global__ void dp_env_table_kernel(DevSlots slots, const double* __restrict__ params, long long B, int n_total,
+                                    double2* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_total) return;
+  const int idx = (int)(i / B);
+  const long long b = i - (long long)idx * B;
   dcplx env[KA];
-};
+  casq_channel_envelopes<KA>(slots, params, B, b, idx, env);
+#pragma unroll
+  for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * B + b] = make_double2(env[k].re, env[k].im);
+}
 
 template <int D, int KA>
-__device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, DpState<D, KA>& st, double t,
-                                       const double* yr, const double* yi, double* kr, double* ki) {
-  const int gidx = dev_sample_index(t, a.dt_sample, a.n_total);
-  if (gidx != st.cur_idx) {
-    st.cur_idx = gidx;
-    casq_channel_envelopes<KA>(a.slots, a.params, a.B, b, gidx, st.env);
-  }
+__device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double t, const double* yr, const double* yi,
+                                       double* kr, double* ki) {
+  const int gidx = dev_sample_index_fast(t, a.dt_sample, a.inv_dt_sample, a.n_total);
+  const bool inside = gidx >= 0 && gidx < a.n_total;
   double zr[KA], zi[KA];
 #pragma unroll
   for (int k = 0; k < KA; k++) {
+    const double2 env = inside ? __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b) : make_double2(0.0, 0.0);
     double s, c;
-    sincos(a.two_pi_nu[k] * t, &s, &c);
-    zr[k] = st.env[k].re * c - st.env[k].im * s;
-    zi[k] = st.env[k].re * s + st.env[k].im * c;
+    dp_sincos(a.two_pi_nu[k] * t, &s, &c);
+    zr[k] = env.x * c - env.y * s;
+    zi[k] = env.x * s + env.y * c;
   }
   double wr[D], wi[D];
 #pragma unroll
@@ -114,7 +165,7 @@ __device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, DpState
           gi += zr[k] * (a.Pi[k][e] + a.Ni[k][e]) + zi[k] * (a.Pr[k][e] - a.Nr[k][e]);
         }
         double s, c;
-        sincos(a.bohr[e] * t, &s, &c);
+        dp_sincos(a.bohr[e] * t, &s, &c);
         const double hr = gr * c - gi * s, hi = gr * s + gi * c;
         wr[i] += hr * yr[j] - hi * yi[j];
         wi[i] += hr * yi[j] + hi * yr[j];
@@ -149,11 +200,6 @@ template <int D, int KA>
 __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.B) return;
-  DpState<D, KA> st;
-  st.cur_idx = -2;
-#pragma unroll
-  for (int k = 0; k < KA; k++) st.env[k].re = st.env[k].im = 0.0;
-
   double yr[D], yi[D];
   {
     const double* src = a.y0 + (a.y0_batched ? b * 2 * D : 0);
@@ -195,7 +241,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
   double t = a.tpts[0];
   // k[0] = f(y0, t0)
   double kr[7][D], ki[7][D];
-  dp_rhs<D, KA>(a, b, st, t, yr, yi, kr[0], ki[0]);
+  dp_rhs<D, KA>(a, b, t, yr, yi, kr[0], ki[0]);
 
   // ---- initial step size (Hairer, Norsett, Wanner II.4; order 4)
   double dt;
@@ -204,7 +250,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
     double sc[D];
 #pragma unroll
     for (int i = 0; i < D; i++) {
-      sc[i] = a.atol + hypot(yr[i], yi[i]) * a.rtol;
+      sc[i] = a.atol + sqrt(yr[i] * yr[i] + yi[i] * yi[i]) * a.rtol;
       d0 += (yr[i] * yr[i] + yi[i] * yi[i]) / (sc[i] * sc[i]);
       d1 += (kr[0][i] * kr[0][i] + ki[0][i] * ki[0][i]) / (sc[i] * sc[i]);
     }
@@ -217,7 +263,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       tr[i] = yr[i] + h0 * kr[0][i];
       ti[i] = yi[i] + h0 * ki[0][i];
     }
-    dp_rhs<D, KA>(a, b, st, t + h0, tr, ti, fr, fi);
+    dp_rhs<D, KA>(a, b, t + h0, tr, ti, fr, fi);
     double d2 = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -264,7 +310,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
         tr[i] = yr[i] + dt * ar;
         ti[i] = yi[i] + dt * ai;
       }
-      dp_rhs<D, KA>(a, b, st, t + dt * DP_ALPHA[s - 1], tr, ti, kr[s], ki[s]);
+      dp_rhs<D, KA>(a, b, t + dt * DP_ALPHA[s - 1], tr, ti, kr[s], ki[s]);
     }
     double y1r[D], y1i[D];
     double ratio = 0;
@@ -283,7 +329,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       y1i[i] = dt * si + yi[i];
       er *= dt;
       ei *= dt;
-      const double tol = a.atol + a.rtol * fmax(hypot(yr[i], yi[i]), hypot(y1r[i], y1i[i]));
+      const double tol = a.atol + a.rtol * sqrt(fmax(yr[i] * yr[i] + yi[i] * yi[i], y1r[i] * y1r[i] + y1i[i] * y1i[i]));
       ratio += (er * er + ei * ei) / (tol * tol);
     }
     ratio = sqrt(ratio / D);
@@ -446,9 +492,23 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
   a.out = out_dev;
   a.nsteps = (long long*)nsteps_dev;
   a.status = status_dev;
-  a.slots = ds;
   a.n_total = n_total;
   a.dt_sample = m->dt;
+  a.inv_dt_sample = 1.0 / m->dt;
+  {
+    const size_t n_tab = (size_t)KA * std::max(n_total, 1) * (size_t)B;
+    if ((rc = m->work2.ensure(n_tab * sizeof(double2)))) return rc;
+    a.env_tab = (const double2*)m->work2.p;
+    const long long n = (long long)B * n_total;
+    if (n > 0) {
+      const unsigned g = (unsigned)((n + 255) / 256);
+      if (KA == 1)
+        dp_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
+      else
+        dp_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
+      CASQ_CUDA(cudaGetLastError());
+    }
+  }
   a.rtol = rtol;
   a.atol = atol;
   a.hmax = (hmax > 0) ? hmax : INFINITY;
