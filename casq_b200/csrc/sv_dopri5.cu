@@ -80,27 +80,31 @@ __device__ __forceinline__ int dev_sample_index_fast(double t, double dt, double
 
 // Branch-free fp64 sincos for |x| < 1e5 (phases reach ~2e3 rad here): two-FMA Cody-Waite reduction by pi/2 and the
 // fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The library sincos hides a slow-path branch in every call,
-// which keeps the compiler from overlapping the carrier and Bohr-phase evaluations of a stage.
-__device__ __forceinline__ void dp_sincos(double x, double* sn, double* cs) {
-  if (fabs(x) >= 1.0e5) {
-    sincos(x, sn, cs);
-    return;
-  }
-  const double n = rint(x * 6.36619772367581382433e-01);
-  double r = fma(-n, 1.5707963267948966, x);
-  r = fma(-n, 6.123233995736766e-17, r);
+// which keeps the compiler from overlapping the carrier and Bohr-phase evaluations of a stage; callers test the
+// argument range once for all phases of a stage (DP_TRIG_MAX).  Coefficients live in constant memory so that every
+// DFMA takes its constant straight from the bank (as 64-bit immediates each one cost two UMOV per use).
+#define DP_TRIG_MAX 1.0e5
+__constant__ double DP_TRIG[16] = {6.36619772367581382433e-01, 1.5707963267948966, 6.123233995736766e-17, 0.0,
+                                   1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                   -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+                                   -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                   2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__device__ __forceinline__ void dp_sincos_fast(double x, double* sn, double* cs) {
+  const double n = rint(x * DP_TRIG[0]);
+  double r = fma(-n, DP_TRIG[1], x);
+  r = fma(-n, DP_TRIG[2], r);
   const double z = r * r;
-  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = fma(z, ps, 2.75573137070700676789e-06);
-  ps = fma(z, ps, -1.98412698298579493134e-04);
-  ps = fma(z, ps, 8.33333333332248946124e-03);
-  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double ps = fma(z, DP_TRIG[4], DP_TRIG[5]);
+  ps = fma(z, ps, DP_TRIG[6]);
+  ps = fma(z, ps, DP_TRIG[7]);
+  ps = fma(z, ps, DP_TRIG[8]);
+  ps = fma(z, ps, DP_TRIG[9]);
   const double sr = fma(z * r, ps, r);
-  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = fma(z, pc, -2.75573143513906633035e-07);
-  pc = fma(z, pc, 2.48015872894767294178e-05);
-  pc = fma(z, pc, -1.38888888888741095749e-03);
-  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double pc = fma(z, DP_TRIG[10], DP_TRIG[11]);
+  pc = fma(z, pc, DP_TRIG[12]);
+  pc = fma(z, pc, DP_TRIG[13]);
+  pc = fma(z, pc, DP_TRIG[14]);
+  pc = fma(z, pc, DP_TRIG[15]);
   const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
   const int q = (int)n;
   const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
@@ -125,21 +129,45 @@ __global__ void dp_env_table_kernel(DevSlots slots, const double* __restrict__ p
   for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * B + b] = make_double2(env[k].re, env[k].im);
 }
 
+// Everything of the right-hand side that depends on t only: h_d[i] (real diagonal) and the upper-triangle elements
+// h[e] = (S + sum_k z_k P_k + conj(z_k) N_k)[i,j] e^{i(e_i - e_j)t} of the frame-rotated Hamiltonian.
+template <int D>
+struct DpCoef {
+  double hd[D];
+  double hr[D * (D - 1) / 2], hi[D * (D - 1) / 2];
+};
+
 template <int D, int KA>
-__device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double t, const double* yr, const double* yi,
-                                       double* kr, double* ki) {
+__device__ __forceinline__ void dp_coef(const Dopri5Args& a, long long b, double t, DpCoef<D>& cf) {
+  constexpr int E = D * (D - 1) / 2;
   const int gidx = dev_sample_index_fast(t, a.dt_sample, a.inv_dt_sample, a.n_total);
   const bool inside = gidx >= 0 && gidx < a.n_total;
+  double2 env[KA];
+#pragma unroll
+  for (int k = 0; k < KA; k++)
+    env[k] = inside ? __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b) : make_double2(0.0, 0.0);
+  // phases: carriers first, then the Bohr frequencies of the populated elements
+  double x[KA + E], sn[KA + E], cs[KA + E];
+  double xmax = 0.0;
+#pragma unroll
+  for (int k = 0; k < KA; k++) x[k] = a.two_pi_nu[k] * t;
+#pragma unroll
+  for (int e = 0; e < E; e++) x[KA + e] = (a.emask & (1u << e)) ? a.bohr[e] * t : 0.0;
+#pragma unroll
+  for (int n = 0; n < KA + E; n++) xmax = fmax(xmax, fabs(x[n]));
+  if (xmax < DP_TRIG_MAX) {
+#pragma unroll
+    for (int n = 0; n < KA + E; n++) dp_sincos_fast(x[n], &sn[n], &cs[n]);
+  } else {
+#pragma unroll
+    for (int n = 0; n < KA + E; n++) sincos(x[n], &sn[n], &cs[n]);
+  }
   double zr[KA], zi[KA];
 #pragma unroll
   for (int k = 0; k < KA; k++) {
-    const double2 env = inside ? __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b) : make_double2(0.0, 0.0);
-    double s, c;
-    dp_sincos(a.two_pi_nu[k] * t, &s, &c);
-    zr[k] = env.x * c - env.y * s;
-    zi[k] = env.x * s + env.y * c;
+    zr[k] = env[k].x * cs[k] - env[k].y * sn[k];
+    zi[k] = env[k].x * sn[k] + env[k].y * cs[k];
   }
-  double wr[D], wi[D];
 #pragma unroll
   for (int i = 0; i < D; i++) {
     double h = 0.0;
@@ -148,25 +176,39 @@ __device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double 
 #pragma unroll
       for (int k = 0; k < KA; k++) h += 2.0 * (zr[k] * a.Pdr[k][i] - zi[k] * a.Pdi[k][i]);
     }
-    wr[i] = h * yr[i];
-    wi[i] = h * yi[i];
+    cf.hd[i] = h;
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    double gr = a.Sr[e], gi = a.Si[e];
+#pragma unroll
+    for (int k = 0; k < KA; k++) {
+      // z*P + conj(z)*N
+      gr += zr[k] * (a.Pr[k][e] + a.Nr[k][e]) - zi[k] * (a.Pi[k][e] - a.Ni[k][e]);
+      gi += zr[k] * (a.Pi[k][e] + a.Ni[k][e]) + zi[k] * (a.Pr[k][e] - a.Nr[k][e]);
+    }
+    cf.hr[e] = gr * cs[KA + e] - gi * sn[KA + e];
+    cf.hi[e] = gr * sn[KA + e] + gi * cs[KA + e];
+  }
+}
+
+// k = -i H y
+template <int D>
+__device__ __forceinline__ void dp_apply(unsigned emask, const DpCoef<D>& cf, const double* yr, const double* yi, double* kr,
+                                         double* ki) {
+  double wr[D], wi[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    wr[i] = cf.hd[i] * yr[i];
+    wi[i] = cf.hd[i] * yi[i];
   }
   int e = 0;
 #pragma unroll
   for (int i = 0; i < D; i++) {
 #pragma unroll
     for (int j = i + 1; j < D; j++) {
-      if (a.emask & (1u << e)) {
-        double gr = a.Sr[e], gi = a.Si[e];
-#pragma unroll
-        for (int k = 0; k < KA; k++) {
-          // z*P + conj(z)*N
-          gr += zr[k] * (a.Pr[k][e] + a.Nr[k][e]) - zi[k] * (a.Pi[k][e] - a.Ni[k][e]);
-          gi += zr[k] * (a.Pi[k][e] + a.Ni[k][e]) + zi[k] * (a.Pr[k][e] - a.Nr[k][e]);
-        }
-        double s, c;
-        dp_sincos(a.bohr[e] * t, &s, &c);
-        const double hr = gr * c - gi * s, hi = gr * s + gi * c;
+      if (emask & (1u << e)) {
+        const double hr = cf.hr[e], hi = cf.hi[e];
         wr[i] += hr * yr[j] - hi * yi[j];
         wi[i] += hr * yi[j] + hi * yr[j];
         wr[j] += hr * yr[i] + hi * yi[i];
@@ -180,6 +222,14 @@ __device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double 
     kr[i] = wi[i];
     ki[i] = -wr[i];
   }
+}
+
+template <int D, int KA>
+__device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double t, const double* yr, const double* yi,
+                                       double* kr, double* ki) {
+  DpCoef<D> cf;
+  dp_coef<D, KA>(a, b, t, cf);
+  dp_apply<D>(a.emask, cf, yr, yi, kr, ki);
 }
 
 __constant__ double DP_ALPHA[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
@@ -295,7 +345,13 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       status = 2;
       break;
     }
-    // ---- one attempted step
+    // ---- one attempted step.  The t-only part of the six new stages (five distinct times: stages 5 and 6 are both
+    // at t + dt) is computed first in a ROLLED loop: one copy of the index / table / sincos code instead of six keeps
+    // the step inside the instruction cache (the fully unrolled step spent 25 % of its cycles on instruction fetch
+    // with one warp per scheduler), and the five sets wait in local memory.
+    DpCoef<D> cfs[5];
+#pragma unroll 1
+    for (int s = 0; s < 5; s++) dp_coef<D, KA>(a, b, t + dt * DP_ALPHA[s], cfs[s]);
 #pragma unroll
     for (int s = 1; s < 7; s++) {
       double tr[D], ti[D];
@@ -310,7 +366,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
         tr[i] = yr[i] + dt * ar;
         ti[i] = yi[i] + dt * ai;
       }
-      dp_rhs<D, KA>(a, b, t + dt * DP_ALPHA[s - 1], tr, ti, kr[s], ki[s]);
+      dp_apply<D>(a.emask, cfs[s < 6 ? s - 1 : 4], tr, ti, kr[s], ki[s]);
     }
     double y1r[D], y1i[D];
     double ratio = 0;
