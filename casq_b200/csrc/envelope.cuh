@@ -77,3 +77,19 @@ __device__ __forceinline__ void casq_channel_envelopes(const DevSlots& s, const 
       }
   }
 }
+
+// Envelope samples of every trajectory, evaluated once per solve: out[k][idx][b], idx in [0, n_total).  Used by the
+// steppers whose lanes sit at DIFFERENT sample indices (adaptive Dopri5) or that need a new sample on every step
+// (propagators with one step per sample): a coalesced 16 B look-up replaces 2 exp + sincos + divisions per call.
+template <int KA>
+__global__ void casq_env_table_kernel(DevSlots slots, const double* __restrict__ params, long long B, int n_total,
+                                      double2* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_total) return;
+  const int idx = (int)(i / B);
+  const long long b = i - (long long)idx * B;
+  dcplx env[KA];
+  casq_channel_envelopes<KA>(slots, params, B, b, idx, env);
+#pragma unroll
+  for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * B + b] = make_double2(env[k].re, env[k].im);
+}

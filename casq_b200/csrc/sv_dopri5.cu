@@ -32,7 +32,7 @@ struct Dopri5Args {
   double* out;        // [B][T_out][D] c128
   long long* nsteps;  // [B][2] attempted, accepted (may be NULL)
   int* status;        // [B] 0 ok, 1 mxstep hit, 2 dt underflow (may be NULL)
-  const double2* env_tab;  // [KA][n_total][B] envelope samples of every trajectory (dp_env_table_kernel)
+  const double2* env_tab;  // [KA][n_total][B] envelope samples of every trajectory (casq_env_table_kernel)
   int n_total;
   double dt_sample, inv_dt_sample;
   double rtol, atol, hmax;
@@ -112,22 +112,9 @@ __device__ __forceinline__ void dp_sincos_fast(double x, double* sn, double* cs)
   *cs = ((q + 1) & 2) ? -c0 : c0;
 }
 
-// Envelope samples of every trajectory, evaluated once per solve: with per-thread stage times almost every RHS call
-// of a warp has SOME lane crossing a sample boundary, so the on-the-fly evaluation (2 exp, sincos, divisions) ran on
-// every call; a look-up in a [KA][n_total][B] table (neighbouring lanes sit in the same or adjacent samples: coalesced)
-// replaces it.
-template <int KA>
-__global__ void dp_env_table_kernel(DevSlots slots, const double* __restrict__ params, long long B, int n_total,
-                                    double2* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * n_total) return;
-  const int idx = (int)(i / B);
-  const long long b = i - (long long)idx * B;
-  dcplx env[KA];
-  casq_channel_envelopes<KA>(slots, params, B, b, idx, env);
-#pragma unroll
-  for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * B + b] = make_double2(env[k].re, env[k].im);
-}
+// Envelope samples come from a per-solve table (casq_env_table_kernel, envelope.cuh): with per-thread stage times
+// almost every RHS call of a warp has SOME lane crossing a sample boundary, so the on-the-fly evaluation (2 exp,
+// sincos, divisions) ran on every call.  Neighbouring lanes sit in the same or adjacent samples: coalesced look-ups.
 
 // Everything of the right-hand side that depends on t only: h_d[i] (real diagonal) and the upper-triangle elements
 // h[e] = (S + sum_k z_k P_k + conj(z_k) N_k)[i,j] e^{i(e_i - e_j)t} of the frame-rotated Hamiltonian.
@@ -559,9 +546,9 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     if (n > 0) {
       const unsigned g = (unsigned)((n + 255) / 256);
       if (KA == 1)
-        dp_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
+        casq_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
       else
-        dp_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
+        casq_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
       CASQ_CUDA(cudaGetLastError());
     }
   }

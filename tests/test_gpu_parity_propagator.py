@@ -65,3 +65,23 @@ def test_propagator_agrees_with_ode_solution():
         U = engine.propagators_expm(nm, [("drag", 0, 0, 24)], engine.pack_params([p], device="cuda"), (0.0, 24 * DT), DT / sub).cpu().numpy()
         errs.append(np.abs(U[0] @ np.array([1, 0, 0]) - truth[0, -1]).max())
     assert errs[0] / errs[1] > 3 and errs[1] / errs[2] > 3 and errs[2] < 1e-4  # second-order scheme
+
+
+@pytest.mark.parametrize("rwa", [None, 3.0e9])
+def test_propagators_match_oracle_d9_all_pade_orders(rwa):
+    """Two coupled transmons (the compile-time d = 9 kernel with the register-resident Gauss-Jordan), two driven channels;
+    max_dt spans the Pade orders 3..9 and the scaled-and-squared regime; B = 7 leaves the last block partly empty."""
+    rng = np.random.default_rng(11)
+    st, ops, ch, _ = O.parse_hamiltonian_dict(_two_transmon_dict(), None)
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st, rwa_cutoff_freq=rwa)
+    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st, rwa_cutoff_freq=rwa)
+    B, dur = 7, 10
+    specs = [O.PulseSpec("gaussian_square", "u0", dur), O.PulseSpec("drag", "d1", dur)]
+    ps = [dict(amp=rng.uniform(0.2, 1.0, B), angle=rng.uniform(-1, 1, B), sigma=3.0, width=rng.uniform(0, 6, B)),
+          dict(amp=rng.uniform(0.1, 0.6, B), angle=rng.uniform(-1, 1, B), sigma=3.0, beta=rng.uniform(-2, 2, B))]
+    samples = O.channel_samples(ch, specs, ps)
+    slots = [("gaussian_square", ch.index("u0"), 0, dur), ("drag", ch.index("d1"), 0, dur)]
+    for max_dt in (DT / 64, DT / 8, DT, 5 * DT):
+        want = O.expm_midpoint_propagators(om, samples, (0.0, dur * DT), max_dt)
+        got = engine.propagators_expm(nm, slots, engine.pack_params(ps, device="cuda"), (0.0, dur * DT), max_dt).cpu().numpy()
+        assert np.abs(got - want).max() < TOL_U, (rwa, max_dt)
