@@ -34,6 +34,8 @@ struct PropArgs {
   const double2* N;
   int identityU;
   const double2* U;  // frame basis
+  const double2* env_tab;  // [KA][n_total][B] envelope samples (casq_env_table_kernel)
+  int n_total;
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -312,32 +314,26 @@ __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_e
   for (int e = lane; e < n2; e += 32) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
   __syncwarp();
 
-  int cur_idx = -2;
-  dcplx env[PROP_MAXK];
-#pragma unroll
-  for (int k = 0; k < PROP_MAXK; k++) env[k].re = env[k].im = 0.0;
-
   long long pos = 0;
   for (int p = 0; p < a.n_pieces; p++) {
     const int n = a.piece_n[p];
     const double h = a.piece_h[p];
     for (int s = 0; s < n; s++) {
       const long long pm = pos + 1;  // midpoint entry
+      // envelope samples come from the per-solve table: with one step per sample (m = 1) the on-the-fly evaluation
+      // (2 exp, sincos, divisions) ran on every step
       const int gidx = __ldg(a.idx + pm);
-      if (gidx != cur_idx) {
-        cur_idx = gidx;
-        casq_channel_envelopes<PROP_MAXK>(a.slots, a.params, a.B, b, gidx, env);
-      }
+      const bool inside = gidx >= 0 && gidx < a.n_total;
       const double* ent = a.table + pm * a.W;
       double zr[PROP_MAXK], zi[PROP_MAXK];
 #pragma unroll
       for (int k = 0; k < PROP_MAXK; k++) {
-        if (k < KA) {
+        zr[k] = zi[k] = 0.0;
+        if (k < KA && inside) {
+          const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
           const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
-          zr[k] = env[k].re * c - env[k].im * sn;
-          zi[k] = env[k].re * sn + env[k].im * c;
-        } else {
-          zr[k] = zi[k] = 0.0;
+          zr[k] = env.x * c - env.y * sn;
+          zi[k] = env.x * sn + env.y * c;
         }
       }
       const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
@@ -486,6 +482,23 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
   a.N = a.P + (size_t)KA * n2;
   a.U = a.N + (size_t)KA * n2;
   a.identityU = m->U_is_identity ? 1 : 0;
+  {
+    const size_t n_tab = (size_t)KA * std::max(n_total, 1) * (size_t)B;
+    if ((rc = m->work2.ensure(n_tab * sizeof(double2)))) return rc;
+    const long long n = (long long)B * n_total;
+    if (n > 0) {
+      const unsigned g = (unsigned)((n + 255) / 256);
+      switch (KA) {
+        case 1: casq_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
+        case 2: casq_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
+        case 3: casq_env_table_kernel<3><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
+        default: casq_env_table_kernel<4><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
+      }
+      CASQ_CUDA(cudaGetLastError());
+    }
+    a.env_tab = (const double2*)m->work2.p;
+    a.n_total = n_total;
+  }
   const size_t smem = (size_t)PROP_WARPS * PROP_NBUF * n2 * sizeof(double2);
   const unsigned grid = (unsigned)((B + PROP_WARPS - 1) / PROP_WARPS);
   // the dimensions transmon models produce get compile-time loop bounds (index arithmetic was 80 % of the generic kernel)
