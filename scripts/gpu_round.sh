@@ -14,6 +14,13 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2
 ncu --set full --clock-control none --import-source on -k regex:sv_rk4_small -s 3 -c 1 -o gpurun_out/prof_rk4 -f \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 python scripts/gpu_time_lindblad.py 64 > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"lindblad_spmm|lindblad_combine|lindblad_coef" -s 210 -c 3 -o gpurun_out/prof_lindblad -f \
+ncu --set full --clock-control none --import-source on -k regex:"lindblad_stage|lindblad_coef" -s 210 -c 5 -o gpurun_out/prof_lindblad -f \
     python scripts/gpu_time_lindblad.py 64 > gpurun_out/ncu_lb.log 2>&1
+python scripts/gpu_time_expm.py > gpurun_out/plain4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:propagator_expm -c 1 -o gpurun_out/prof_expm -f \
+    python scripts/gpu_time_expm.py > gpurun_out/ncu_expm.log 2>&1
+python scripts/gpu_time_dopri5.py > gpurun_out/plain5.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:sv_dopri5 -c 1 -o gpurun_out/prof_dopri5 -f \
+    python scripts/gpu_time_dopri5.py > gpurun_out/ncu_dp5.log 2>&1
+cat gpurun_out/plain3.log gpurun_out/plain4.log gpurun_out/plain5.log
 ls -la gpurun_out | head -30
