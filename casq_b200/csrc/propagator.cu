@@ -6,8 +6,9 @@
 // (src/casq/backends/pulse_backend.py:60-71), so this entry point is additive API for BASELINE cfg 3
 // ("2 coupled transmons (dim 9) cross-resonance GaussianSquare sweep via full-unitary propagator batches").
 // expm is the scaling-and-squaring Pade approximant of Higham (2005) -- the algorithm behind
-// jax.scipy.linalg.expm: order m in {3,5,7,9,13} chosen from ||A||_1, [m/m] Pade solved by Gaussian
-// elimination with partial pivoting, then s squarings.  d < 16 here, so this is CUDA-core complex arithmetic;
+// jax.scipy.linalg.expm: order m in {3,5,7,9} chosen from ||A||_1 (above theta_9 the matrix is scaled to theta_9;
+// Higham's [13/13] branch needs three more live matrices, see wexpm), [m/m] Pade solved by Gaussian elimination with
+// partial pivoting, then s squarings.  d < 16 here, so this is CUDA-core complex arithmetic;
 // a split-complex tensor-core GEMM only pays for d >= 16 (north_star) and is not built.
 #include <algorithm>
 #include <cstring>
