@@ -332,3 +332,33 @@ def test_discretize_matches_oracle_signals():
     assert np.abs(sigs[0].q_signal.samples - (want.imag - 1j * want.real)).max() < 1e-14
     assert sigs[0].i_signal.carrier_freq == pytest.approx(2 * 4.96e9) and not sigs[1].signal.samples.any()
     assert discretize(sched, DT, {"d0": 4.96e9}, carrier_frequency=1e8)[0].carrier == 1e8
+
+
+def test_dopri5_late_window_and_exact_sample_boundaries():
+    """(i) A pulse played 30 000 samples into the schedule: carrier phases pass 1e5 rad, where the branch-free sincos of
+    the Dopri5 kernel hands over to the library one.  (ii) hmax = dt/2 with a wide tolerance makes most steps end EXACTLY
+    on multiples of dt/2 accumulated in floating point: the FMA-corrected sample index must agree with numpy's
+    floor-division on those boundary times (a wrong index is a 1e-2 error here, not a rounding one)."""
+    om, nm, ch = _models((0,), "full")
+    start, dur = 30000, 12
+    p = dict(amp=np.array([0.5, 0.9]), angle=np.array([0.2, -0.7]))
+    samples = O.channel_samples(ch, [O.PulseSpec("constant", "d0", dur + 4, start)], [p])
+    span = (start * DT, (start + dur) * DT)
+    assert 2 * np.pi * O.MANILA_CARRIERS["d0"] * span[0] > 1.0e5
+    te = np.linspace(span[0], span[1], 4)
+    _, want, steps = O.dopri5_jax_solve(om, samples, np.array([1, 0, 0]), span, te, rtol=1e-9, atol=1e-9)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("constant", 0, start, dur + 4)], engine.pack_params([p], device="cuda"),
+                                             np.array([1, 0, 0]), span, rtol=1e-9, atol=1e-9, t_eval=te, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)  # smooth inside the window: step-exact
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-10
+    # (ii)
+    rng = np.random.default_rng(5)
+    B, dur = 4, 16
+    p = _rand_params(rng, "drag", B, dur)
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p])
+    span = (0.0, dur * DT)
+    _, want, steps = O.dopri5_jax_solve(om, samples, np.array([1, 0, 0]), span, rtol=1e-3, atol=1e-3, hmax=DT / 2)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("drag", 0, 0, dur)], engine.pack_params([p], device="cuda"), np.array([1, 0, 0]),
+                                             span, rtol=1e-3, atol=1e-3, hmax=DT / 2, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-11
