@@ -5,6 +5,8 @@
 // formulas per SURVEY.md Appendix A.2: midpoint sampling samples[n] = envelope(n + 1/2),
 // lifted(t; mu, t0, sigma) = (g(t) - g(t0)) / (1 - g(t0)), g(x) = exp(-((x-mu)/sigma)^2 / 2).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 struct dcplx {
@@ -78,18 +80,43 @@ __device__ __forceinline__ void casq_channel_envelopes(const DevSlots& s, const 
   }
 }
 
-// Envelope samples of every trajectory, evaluated once per solve: out[k][idx][b], idx in [0, n_total).  Used by the
-// steppers whose lanes sit at DIFFERENT sample indices (adaptive Dopri5) or that need a new sample on every step
-// (propagators with one step per sample): a coalesced 16 B look-up replaces 2 exp + sincos + divisions per call.
+// Envelope samples of the trajectories [b0, b0 + Bc) of a batch of B, evaluated once per solve: out[k][idx][b - b0],
+// idx in [0, n_total).  Used by the steppers whose lanes sit at DIFFERENT sample indices (adaptive Dopri5) or that
+// need a new sample on every step (propagators with one step per sample): a coalesced 16 B look-up replaces 2 exp +
+// sincos + divisions per call.  Callers walk large batches in windows (casq_env_table_window) to bound the table.
+#define CASQ_ENV_TABLE_MAX_BYTES (1ull << 30)
+static inline long long casq_env_table_window(int KA, int n_total, long long B) {
+  unsigned long long cap = CASQ_ENV_TABLE_MAX_BYTES;
+  if (const char* e = getenv("CASQ_ENV_TABLE_MAX_KB")) cap = 1024ull * strtoull(e, nullptr, 10);  // test knob: force several windows
+  const unsigned long long per_point = (unsigned long long)KA * (unsigned long long)(n_total > 0 ? n_total : 1) * 16ull;
+  const long long w = (long long)(cap / per_point);
+  return w < 1 ? 1 : (w < B ? w : B);
+}
+
 template <int KA>
-__global__ void casq_env_table_kernel(DevSlots slots, const double* __restrict__ params, long long B, int n_total,
-                                      double2* __restrict__ out) {
+__global__ void casq_env_table_kernel(DevSlots slots, const double* __restrict__ params, long long B, long long b0, long long Bc,
+                                      int n_total, double2* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * n_total) return;
-  const int idx = (int)(i / B);
-  const long long b = i - (long long)idx * B;
+  if (i >= Bc * n_total) return;
+  const int idx = (int)(i / Bc);
+  const long long bl = i - (long long)idx * Bc;
   dcplx env[KA];
-  casq_channel_envelopes<KA>(slots, params, B, b, idx, env);
+  casq_channel_envelopes<KA>(slots, params, B, b0 + bl, idx, env);
 #pragma unroll
-  for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * B + b] = make_double2(env[k].re, env[k].im);
+  for (int k = 0; k < KA; k++) out[((long long)k * n_total + idx) * Bc + bl] = make_double2(env[k].re, env[k].im);
+}
+
+template <int KMAX>
+static inline cudaError_t casq_launch_env_table(int KA, DevSlots slots, const double* params, long long B, long long b0, long long Bc,
+                                        int n_total, double2* out, cudaStream_t st) {
+  const long long n = Bc * n_total;
+  if (n <= 0) return cudaSuccess;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  switch (KA) {
+    case 1: casq_env_table_kernel<1><<<g, 256, 0, st>>>(slots, params, B, b0, Bc, n_total, out); break;
+    case 2: casq_env_table_kernel<(KMAX >= 2 ? 2 : 1)><<<g, 256, 0, st>>>(slots, params, B, b0, Bc, n_total, out); break;
+    case 3: casq_env_table_kernel<(KMAX >= 3 ? 3 : 1)><<<g, 256, 0, st>>>(slots, params, B, b0, Bc, n_total, out); break;
+    default: casq_env_table_kernel<(KMAX >= 4 ? 4 : 1)><<<g, 256, 0, st>>>(slots, params, B, b0, Bc, n_total, out); break;
+  }
+  return cudaGetLastError();
 }

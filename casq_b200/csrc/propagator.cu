@@ -483,37 +483,31 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
   a.N = a.P + (size_t)KA * n2;
   a.U = a.N + (size_t)KA * n2;
   a.identityU = m->U_is_identity ? 1 : 0;
-  {
-    const size_t n_tab = (size_t)KA * std::max(n_total, 1) * (size_t)B;
-    if ((rc = m->work2.ensure(n_tab * sizeof(double2)))) return rc;
-    const long long n = (long long)B * n_total;
-    if (n > 0) {
-      const unsigned g = (unsigned)((n + 255) / 256);
-      switch (KA) {
-        case 1: casq_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
-        case 2: casq_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
-        case 3: casq_env_table_kernel<3><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
-        default: casq_env_table_kernel<4><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p); break;
-      }
-      CASQ_CUDA(cudaGetLastError());
-    }
-    a.env_tab = (const double2*)m->work2.p;
-    a.n_total = n_total;
-  }
   const size_t smem = (size_t)PROP_WARPS * PROP_NBUF * n2 * sizeof(double2);
-  const unsigned grid = (unsigned)((B + PROP_WARPS - 1) / PROP_WARPS);
+  // the batch is walked in windows that bound the envelope table
+  const long long Bw = casq_env_table_window(KA, n_total, B);
+  if ((rc = m->work2.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
+  a.env_tab = (const double2*)m->work2.p;
+  a.n_total = n_total;
   // the dimensions transmon models produce get compile-time loop bounds (index arithmetic was 80 % of the generic kernel)
 #define PROP_LAUNCH(DT_)                                                                                              \
   {                                                                                                                   \
     CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     propagator_expm_kernel<DT_><<<grid, 32 * PROP_WARPS, smem, st>>>(a);                                              \
   }
-  switch (d) {
-    case 2: PROP_LAUNCH(2) break;
-    case 3: PROP_LAUNCH(3) break;
-    case 4: PROP_LAUNCH(4) break;
-    case 9: PROP_LAUNCH(9) break;
-    default: PROP_LAUNCH(0) break;
+  for (long long b0 = 0; b0 < B; b0 += Bw) {
+    const long long Bc = std::min(Bw, (long long)B - b0);
+    CASQ_CUDA(casq_launch_env_table<PROP_MAXK>(KA, ds, params_dev, B, b0, Bc, n_total, (double2*)m->work2.p, st));
+    a.B = Bc;
+    a.out = out_dev + b0 * 2LL * n2;
+    const unsigned grid = (unsigned)((Bc + PROP_WARPS - 1) / PROP_WARPS);
+    switch (d) {
+      case 2: PROP_LAUNCH(2) break;
+      case 3: PROP_LAUNCH(3) break;
+      case 4: PROP_LAUNCH(4) break;
+      case 9: PROP_LAUNCH(9) break;
+      default: PROP_LAUNCH(0) break;
+    }
   }
 #undef PROP_LAUNCH
   CASQ_CUDA(cudaGetLastError());

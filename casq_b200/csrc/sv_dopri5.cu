@@ -538,20 +538,6 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
   a.n_total = n_total;
   a.dt_sample = m->dt;
   a.inv_dt_sample = 1.0 / m->dt;
-  {
-    const size_t n_tab = (size_t)KA * std::max(n_total, 1) * (size_t)B;
-    if ((rc = m->work2.ensure(n_tab * sizeof(double2)))) return rc;
-    a.env_tab = (const double2*)m->work2.p;
-    const long long n = (long long)B * n_total;
-    if (n > 0) {
-      const unsigned g = (unsigned)((n + 255) / 256);
-      if (KA == 1)
-        casq_env_table_kernel<1><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
-      else
-        casq_env_table_kernel<2><<<g, 256, 0, st>>>(ds, params_dev, B, n_total, (double2*)m->work2.p);
-      CASQ_CUDA(cudaGetLastError());
-    }
-  }
   a.rtol = rtol;
   a.atol = atol;
   a.hmax = (hmax > 0) ? hmax : INFINITY;
@@ -591,14 +577,27 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     }
   }
   a.identityU = m->U_is_identity ? 1 : 0;
+  // the batch is walked in windows that bound the envelope table (one window up to 2.6e5 points at cfg 5's 257 samples)
+  const long long Bw = casq_env_table_window(KA, n_total, B);
+  if ((rc = m->work2.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
+  a.env_tab = (const double2*)m->work2.p;
   const int block = 64;
-  const unsigned grid = (unsigned)((B + block - 1) / block);
+  for (long long b0 = 0; b0 < B; b0 += Bw) {
+    const long long Bc = std::min(Bw, (long long)B - b0);
+    CASQ_CUDA(casq_launch_env_table<DP_MAXK>(KA, ds, params_dev, B, b0, Bc, n_total, (double2*)m->work2.p, st));
+    a.B = Bc;
+    a.y0 = y0_dev + (y0_batched ? b0 * 2 * d : 0);
+    a.out = out_dev + b0 * (long long)T * 2 * d;
+    a.nsteps = nsteps_dev ? (long long*)nsteps_dev + 2 * b0 : nullptr;
+    a.status = status_dev ? status_dev + b0 : nullptr;
+    const unsigned grid = (unsigned)((Bc + block - 1) / block);
 #define LAUNCH(D_, K_)                                        \
   if (d == D_ && KA == K_) {                                  \
     sv_dopri5_kernel<D_, K_><<<grid, block, 0, st>>>(a);      \
   }
-  LAUNCH(2, 1) LAUNCH(2, 2) LAUNCH(3, 1) LAUNCH(3, 2) LAUNCH(4, 1) LAUNCH(4, 2)
+    LAUNCH(2, 1) LAUNCH(2, 2) LAUNCH(3, 1) LAUNCH(3, 2) LAUNCH(4, 1) LAUNCH(4, 2)
 #undef LAUNCH
+  }
   CASQ_CUDA(cudaGetLastError());
   return CASQ_OK;
 }

@@ -97,3 +97,27 @@ def test_max_slots_and_two_channels_d3(q0):
     _, wantd, _ = O.dopri5_jax_solve(om, samples[:3], np.array([1, 0, 0]), span, rtol=1e-9, atol=1e-9)
     gotd = engine.solve_sv_dopri5(nm, slots, engine.pack_params(ps, device="cuda"), np.array([1, 0, 0]), span, rtol=1e-9, atol=1e-9)
     assert np.abs(gotd.cpu().numpy()[:3] - wantd).max() < 5e-6
+
+
+def test_envelope_table_windows_give_identical_results(monkeypatch):
+    """Dopri5 (d <= 4) and the propagator path look the envelope up in a per-solve table that is built for windows of
+    the batch (bounded memory for huge sweeps).  Forcing 3-point windows must not change a single bit."""
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
+    rng = np.random.default_rng(12)
+    B, dur = 11, 16
+    p = dict(amp=rng.uniform(0.1, 0.9, B), angle=rng.uniform(-1, 1, B), sigma=4.0, beta=rng.uniform(-2, 2, B))
+    pk = engine.pack_params([p], device="cuda")
+    y0 = np.array([1, 0, 0])
+
+    def run():
+        y, ns, stt = engine.solve_sv_dopri5(nm, [("drag", 0, 0, dur)], pk, y0, (0.0, dur * DT), rtol=1e-8, atol=1e-8, return_stats=True)
+        U = engine.propagators_expm(nm, [("drag", 0, 0, dur)], pk, (0.0, dur * DT), DT / 2)
+        return y.clone(), ns.clone(), stt.clone(), U.clone()
+
+    monkeypatch.delenv("CASQ_ENV_TABLE_MAX_KB", raising=False)
+    ref = run()
+    monkeypatch.setenv("CASQ_ENV_TABLE_MAX_KB", "1")  # 1 kB / (16 samples x 16 B) = 4 points per window
+    got = run()
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
