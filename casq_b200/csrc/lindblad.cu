@@ -261,7 +261,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t o_tffreq = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
   const size_t o_ph = off; off = align16(off + (size_t)d * 16);
-  const size_t o_cd = off; off = align16(off + (cdense.empty() ? 16 : (size_t)d * d * 16));
+  const int ld = (d + 7) & ~7;  // 128 B aligned rows: a warp's 512 B gather touches 4 lines, not 5
+  const size_t o_cd = off; off = align16(off + (cdense.empty() ? 16 : (size_t)d * ld * 16));
   const int ntile = (d + LB_TILE - 1) / LB_TILE;
   std::vector<int> pair_ij;
   for (int I = 0; I < ntile; I++)  // off-diagonal pairs (twice the work) first
@@ -290,7 +291,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     memcpy(&blob[o_tffreq], tf_freq.data(), NTF * sizeof(int));
   }
   memcpy(&blob[o_V], m->V.data(), (size_t)d * d * 16);
-  if (!cdense.empty()) memcpy(&blob[o_cd], cdense.data(), (size_t)d * d * 16);
+  if (!cdense.empty())
+    for (int r = 0; r < d; r++) memcpy(&blob[o_cd + (size_t)r * ld * 16], &cdense[(size_t)r * d], (size_t)d * 16);
   memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
 
   const size_t n_per = (size_t)d * d;
@@ -300,7 +302,8 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
   if ((rc = m->work1.ensure(blob.size()))) return rc;
   if (NQ > LB_MAXQ) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "more than %d one-sided shift classes (%d): operators too dense for the structured path", LB_MAXQ, NQ);
-  if ((rc = m->work2.ensure(4 * (size_t)B * n_per * 16))) return rc;
+  const size_t n_pad = (size_t)d * ld;
+  if ((rc = m->work2.ensure(4 * (size_t)B * n_pad * 16))) return rc;
   const size_t n_cq = (size_t)B * NQ * d, n_cu = (size_t)B * std::max(NU, 1) * d;
   if ((rc = m->work3.ensure(3 * (n_cq + n_cu) * 16))) return rc;
   double2* cq_all = (double2*)m->work3.p;
@@ -331,15 +334,15 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   }
   unsigned char* dev = (unsigned char*)m->work1.p;
   double2* bufs[4];  // y, y1, y2, y3
-  for (int i = 0; i < 4; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_per;
+  for (int i = 0; i < 4; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_pad;
   {
     const long long n = (long long)B * n_per;
-    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)n_per, B, (const double2*)rho0_dev, rho0_batched, bufs[0]);
+    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, ld, B, (const double2*)rho0_dev, rho0_batched, bufs[0]);
     CASQ_CUDA(cudaGetLastError());
   }
   LbArgs a;
   memset(&a, 0, sizeof(a));
-  a.d = d; a.B = B;
+  a.d = d; a.ld = ld; a.B = B;
   a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NG = NG; a.NP = (int)grp_pairs.size() / 2; a.W = W;
   a.grp_start = (const int*)(dev + o_gstart);
   a.q_delta = (const int*)(dev + o_qdelta);
@@ -371,7 +374,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   auto emit = [&](double t) -> int {
     if (out_rho_dev) {
       const long long n = (long long)B * n_per;
-      lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((long long)n_per, B, bufs[0], (double2*)out_rho_dev, T, t_slot);
+      lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, ld, B, bufs[0], (double2*)out_rho_dev, T, t_slot);
       CASQ_CUDA(cudaGetLastError());
     }
     if (out_pops_dev) {
@@ -379,7 +382,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
       // synchronous small copy: ph is reused by the next output point
       CASQ_CUDA(cudaMemcpyAsync(dev + o_ph, ph.data(), (size_t)d * 16, cudaMemcpyHostToDevice, st));
       CASQ_CUDA(cudaStreamSynchronize(st));
-      lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)B), 256, 0, st>>>(d, bufs[0], (const double2*)(dev + o_V), (const double2*)(dev + o_ph),
+      lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)B), 256, 0, st>>>(d, ld, bufs[0], (const double2*)(dev + o_V), (const double2*)(dev + o_ph),
                                                                         out_pops_dev, T, t_slot);
       CASQ_CUDA(cudaGetLastError());
     }

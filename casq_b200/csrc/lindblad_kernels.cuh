@@ -22,6 +22,7 @@
 
 struct LbArgs {
   int d;
+  int ld;  // row stride of the density-matrix buffers: d rounded up to 8 elements, so every row starts on a 128 B line
   long long B;
   int KA, NF, NTF, NQ, NU, NG, NP, W;
   const int* q_delta;     // [NQ]
@@ -45,7 +46,7 @@ struct LbArgs {
 struct LbLists {   // per (set, trajectory, row), written by lindblad_coef_kernel
   int* lcnt;       // [3][B][d]       number of one-sided classes acting on the row
   double2* lcoef;  // [3][B][d][NQ]   their coefficients
-  int* loff;       // [3][B][d][NQ]   element offset delta*d of the source row
+  int* loff;       // [3][B][d][NQ]   element offset delta*ld of the source row
   int* gcnt;       // [3][B][d]       number of two-sided gather groups with a non-zero row factor
   int* glist;      // [3][B][d][NG]
 };
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) lindblad_coef_kernel(const LbArgs a, long
       const double2 c = oq[q * d + row];
       if (c.x != 0.0 || c.y != 0.0) {
         lc[k] = c;
-        lo[k] = a.q_delta[q] * d;
+        lo[k] = a.q_delta[q] * a.ld;
         k++;
       }
     }
@@ -132,22 +133,25 @@ struct LbStage {
   double h;
 };
 
-// rho0 broadcast / copy into the working buffer
-__global__ void lindblad_init_kernel(long long n_per, long long B, const double2* __restrict__ rho0, int batched,
+// rho0 broadcast / copy into the (row-padded) working buffer
+__global__ void lindblad_init_kernel(int d, int ld, long long B, const double2* __restrict__ rho0, int batched,
                                      double2* __restrict__ y) {
+  const long long n_per = (long long)d * d;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_per * B) return;
-  y[i] = batched ? rho0[i] : rho0[i % n_per];
+  const long long b = i / n_per, e = i - b * n_per;
+  const int r = (int)(e / d), c = (int)(e - (long long)r * d);
+  y[(b * d + r) * ld + c] = batched ? rho0[i] : rho0[e];
 }
 
 // Observables at one output time: dressed-basis populations p_i = (V^+ rho_lab V)_ii with
 // rho_lab[a,b] = e^{-i(e_a-e_b)t} rho_F[a,b].  One block per (state i, trajectory b).
-__global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, const double2* __restrict__ rho, const double2* __restrict__ V,
+__global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, int ld, const double2* __restrict__ rho, const double2* __restrict__ V,
                                                             const double2* __restrict__ ph /*[d] e^{-i e t}*/,
                                                             double* __restrict__ pops, int T, int t_slot) {
   const int i = blockIdx.x;
   const long long b = blockIdx.y;
-  const double2* R = rho + b * (long long)d * d;
+  const double2* R = rho + b * (long long)d * ld;
   __shared__ double red[256];
   double acc = 0.0;
   for (int arow = threadIdx.x; arow < d; arow += blockDim.x) {
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, const double2
     for (int bc = 0; bc < d; bc++) {
       const double2 v = V[bc * d + i], p = ph[bc];
       const double2 w = make_double2(v.x * p.x + v.y * p.y, v.y * p.x - v.x * p.y);  // V[b,i] conj(ph_b)
-      const double2 x = R[(long long)arow * d + bc];
+      const double2 x = R[(long long)arow * ld + bc];
       sx += x.x * w.x - x.y * w.y;
       sy += x.x * w.y + x.y * w.x;
     }
@@ -172,10 +176,12 @@ __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, const double2
   if (threadIdx.x == 0) pops[(b * T + t_slot) * (long long)d + i] = red[0];
 }
 
-__global__ void lindblad_copy_out_kernel(long long n_per, long long B, const double2* __restrict__ y, double2* __restrict__ out,
+__global__ void lindblad_copy_out_kernel(int d, int ld, long long B, const double2* __restrict__ y, double2* __restrict__ out,
                                          int T, int t_slot) {
+  const long long n_per = (long long)d * d;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_per * B) return;
   const long long b = i / n_per, e = i - b * n_per;
-  out[(b * T + t_slot) * n_per + e] = y[i];
+  const int r = (int)(e / d), c = (int)(e - (long long)r * d);
+  out[(b * T + t_slot) * n_per + e] = y[(b * d + r) * ld + c];
 }

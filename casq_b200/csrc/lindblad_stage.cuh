@@ -28,11 +28,11 @@ struct LbTileShared {  // block-wide group tables
 
 // One output row segment: columns c0 and c0 + 32 of row r.  Lists in shared memory (warp-private).
 template <bool TWO>
-__device__ __forceinline__ void lb_tile_unit(int d, const double2* lc, const int* lo, int cnt, const double2* ul, const int* sg, int gc,
+__device__ __forceinline__ void lb_tile_unit(int d, int ld, const double2* lc, const int* lo, int cnt, const double2* ul, const int* sg, int gc,
                                              const LbTileShared& T, const double2* __restrict__ cdense,
                                              const double2* __restrict__ gu, const double2* __restrict__ in, int r, int c0, bool ok0,
                                              bool ok1, double w, double2& o0, double2& o1) {
-  const int e0 = r * d + c0;  // d <= 1024: element indices of one matrix fit 32 bits
+  const int e0 = r * ld + c0;  // d <= 1024: element indices of one matrix fit 32 bits
   const double2* pc = in + e0;
   asm volatile("" : "+l"(pc));  // keep the lane's base pointer in registers: one IMAD.WIDE per gather
   const double2 z = make_double2(0.0, 0.0);
@@ -67,7 +67,7 @@ __device__ __forceinline__ void lb_tile_unit(int d, const double2* lc, const int
       // coefficient (their right factor is zero) and are not loaded.
       const int g = sg[kk];
       const int cc0 = c0 + T.gd2[g], cc1 = cc0 + 32;
-      const double2* prow = in + (r + T.gd1[g]) * d;
+      const double2* prow = in + (r + T.gd1[g]) * ld;
       const double2 v0 = (ok0 && (unsigned)cc0 < (unsigned)d) ? __ldg(prow + cc0) : z;
       const double2 v1 = (ok1 && (unsigned)cc1 < (unsigned)d) ? __ldg(prow + cc1) : z;
       double g0x = 0.0, g0y = 0.0, g1x = 0.0, g1y = 0.0;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
                                                                 const LbStage s) {
   extern __shared__ __align__(16) unsigned char lb_smem[];
   __shared__ LbTileShared T;
-  const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = a.d, ld = a.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int NQs = (a.NQ + 3) & ~3, NUs = a.NU > 0 ? a.NU : 1, NGs = a.NG > 0 ? a.NG : 1;
   double2(*s_T)[LB_TPAD] = reinterpret_cast<double2(*)[LB_TPAD]>(lb_smem);          // [64][65]
   double2* dbase = reinterpret_cast<double2*>(lb_smem) + LB_TILE * LB_TPAD;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
     T.gd1[threadIdx.x] = a.u_delta[a.grp_pairs[2 * p0]];
     T.gd2[threadIdx.x] = a.u_delta[a.grp_pairs[2 * p0 + 1]];
   }
-  const long long base = b * (long long)d * d;
+  const long long base = b * (long long)d * ld;
   const double2* in = s.in + base;
   const double2* gu = cu + ((long long)set * a.B + b) * a.NU * d;
   const long long rowbase = ((long long)set * a.B + b) * d;
@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
     double2 o0 = make_double2(0.0, 0.0), o1 = o0;
     if (r < d) {
       if (diag)
-        lb_tile_unit<true>(d, lc + u * NQs, lo + u * NQs, cnt, ul + u * NUs, sg + u * NGs, gc, T, a.cdense, gu, in, r, cI, okI0, okI1, w, o0, o1);
+        lb_tile_unit<true>(d, ld, lc + u * NQs, lo + u * NQs, cnt, ul + u * NUs, sg + u * NGs, gc, T, a.cdense, gu, in, r, cI, okI0, okI1, w, o0, o1);
       else
-        lb_tile_unit<false>(d, lc + (4 + u) * NQs, lo + (4 + u) * NQs, cnt, nullptr, nullptr, 0, T, nullptr, gu, in, r, cI, okI0, okI1, w, o0, o1);
+        lb_tile_unit<false>(d, ld, lc + (4 + u) * NQs, lo + (4 + u) * NQs, cnt, nullptr, nullptr, 0, T, nullptr, gu, in, r, cI, okI0, okI1, w, o0, o1);
     }
     s_T[x][lane] = o0;
     s_T[x][lane + 32] = o1;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
     const int cnt = __shfl_sync(0xffffffffu, mycnt, u), gc = __shfl_sync(0xffffffffu, mycnt, 8 + u);
     if (r >= d) continue;  // warp-uniform
     // step-start values first: their HBM latency overlaps the gathers below
-    const long long o = base + (long long)r * d + cJ;
+    const long long o = base + (long long)r * ld + cJ;
     const double2 zz = make_double2(0.0, 0.0);
     const double2 y00 = okJ0 ? s.y[o] : zz, y01 = okJ1 ? s.y[o + 32] : zz;
     double2 o0, o1;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
       o0 = s_T[x][lane];
       o1 = s_T[x][lane + 32];
     } else {
-      lb_tile_unit<true>(d, lc + u * NQs, lo + u * NQs, cnt, ul + u * NUs, sg + u * NGs, gc, T, a.cdense, gu, in, r, cJ, okJ0, okJ1, w, o0, o1);
+      lb_tile_unit<true>(d, ld, lc + u * NQs, lo + u * NQs, cnt, ul + u * NUs, sg + u * NGs, gc, T, a.cdense, gu, in, r, cJ, okJ0, okJ1, w, o0, o1);
     }
     if (okJ0) {
       const double2 t = s_T[lane][x];  // M_JI(rJ + lane, rI + x)
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(512, 2) lindblad_stage_kernel(const LbArgs a, 
   for (int u = 0; u < 4; u++) {
     const int x = warp + 16 * u, r = rJ + x;
     if (r < d) {
-      const long long o = base + (long long)r * d + cI;
+      const long long o = base + (long long)r * ld + cI;
       if (okI0) {
         const double2 t = s_T[x][lane];
         s.out[o] = make_double2(t.x, -t.y);
