@@ -260,7 +260,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t o_tfsig = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_tffreq = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
-  const size_t o_ph = off; off = align16(off + (size_t)d * 16);
+  const size_t o_ph = off; off = align16(off + (size_t)std::max(T, 1) * d * 16);  // e^{-i e t} for every output time
   const int ld = (d + 7) & ~7;  // 128 B aligned rows: a warp's 512 B gather touches 4 lines, not 5
   const size_t o_cd = off; off = align16(off + (cdense.empty() ? 16 : (size_t)d * ld * 16));
   const int ntile = (d + LB_TILE - 1) / LB_TILE;
@@ -291,6 +291,15 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     memcpy(&blob[o_tffreq], tf_freq.data(), NTF * sizeof(int));
   }
   memcpy(&blob[o_V], m->V.data(), (size_t)d * d * 16);
+  {
+    cplx* ph = reinterpret_cast<cplx*>(&blob[o_ph]);
+    int slot = 0;
+    for (size_t i = 0; i < g.out_times.size() && slot < T; i++)
+      if (g.out_keep[i]) {
+        for (int e = 0; e < d; e++) ph[(size_t)slot * d + e] = std::polar(1.0, -m->fe[e] * g.out_times[i]);
+        slot++;
+      }
+  }
   if (!cdense.empty())
     for (int r = 0; r < d; r++) memcpy(&blob[o_cd + (size_t)r * ld * 16], &cdense[(size_t)r * d], (size_t)d * 16);
   memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
@@ -369,27 +378,23 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   const size_t smem_stage = lindblad_stage_smem(NQ, NU, NG);
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
 
-  std::vector<cplx> ph(d);
   int t_slot = 0;
-  auto emit = [&](double t) -> int {
+  auto emit = [&]() -> int {
     if (out_rho_dev) {
       const long long n = (long long)B * n_per;
       lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, ld, B, bufs[0], (double2*)out_rho_dev, T, t_slot);
       CASQ_CUDA(cudaGetLastError());
     }
     if (out_pops_dev) {
-      for (int i = 0; i < d; i++) ph[i] = std::polar(1.0, -m->fe[i] * t);
-      // synchronous small copy: ph is reused by the next output point
-      CASQ_CUDA(cudaMemcpyAsync(dev + o_ph, ph.data(), (size_t)d * 16, cudaMemcpyHostToDevice, st));
-      CASQ_CUDA(cudaStreamSynchronize(st));
-      lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)B), 256, 0, st>>>(d, ld, bufs[0], (const double2*)(dev + o_V), (const double2*)(dev + o_ph),
-                                                                        out_pops_dev, T, t_slot);
+      lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)B), 256, 0, st>>>(d, ld, bufs[0], (const double2*)(dev + o_V),
+                                                                        (const double2*)(dev + o_ph) + (size_t)t_slot * d, out_pops_dev, T,
+                                                                        t_slot);
       CASQ_CUDA(cudaGetLastError());
     }
     t_slot++;
     return CASQ_OK;
   };
-  if (g.out_keep[0] && (rc = emit(g.out_times[0]))) return rc;
+  if (g.out_keep[0] && (rc = emit())) return rc;
   long long pos = 0;
   for (size_t p = 0; p < g.piece_nsteps.size(); p++) {
     const int n = g.piece_nsteps[p];
@@ -414,7 +419,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     }
     CASQ_CUDA(cudaGetLastError());
     pos += 1;
-    if (g.out_keep[p + 1] && (rc = emit(g.out_times[p + 1]))) return rc;
+    if (g.out_keep[p + 1] && (rc = emit())) return rc;
   }
   return CASQ_OK;
 }
