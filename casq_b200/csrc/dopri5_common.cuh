@@ -1,0 +1,66 @@
+// casq_b200: pieces shared by the two adaptive Dopri5 steppers (thread per trajectory, d <= 4; warp per trajectory,
+// d <= 64): the sample index of a per-trajectory time and a branch-free fp64 sincos.
+#pragma once
+#include "common.cuh"
+
+// numpy float floor-division a // b (b > 0), then clip to [-1, n_total]
+__device__ __forceinline__ int dev_sample_index(double t, double dt, int n_total) {
+  double mod = fmod(t, dt);
+  double div = (t - mod) / dt;
+  if (mod != 0.0 && (mod < 0)) div -= 1.0;
+  double fl = 0.0;
+  if (div != 0.0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  }
+  if (fl < -1.0) fl = -1.0;
+  if (fl > (double)n_total) fl = (double)n_total;
+  return (int)fl;
+}
+
+// The same index without the iterative fmod: a guess from one multiplication, corrected by the EXACT sign of the
+// remainder t - q dt (one FMA).  Only a remainder that rounds to exactly dt is ambiguous; that case (times that are
+// exact multiples of dt) takes the reference path above.
+__device__ __forceinline__ int dev_sample_index_fast(double t, double dt, double inv_dt, int n_total) {
+  double q = floor(t * inv_dt);
+  const double r = fma(-q, dt, t);
+  if (r == dt) return dev_sample_index(t, dt, n_total);
+  q += (r < 0.0) ? -1.0 : (r > dt ? 1.0 : 0.0);
+  q = fmin(fmax(q, -1.0), (double)n_total);
+  return (int)q;
+}
+
+// Branch-free fp64 sincos for |x| < 1e5 (phases reach ~2e3 rad here): two-FMA Cody-Waite reduction by pi/2 and the
+// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp).  The library sincos hides a slow-path branch in every call,
+// which keeps the compiler from overlapping the carrier and Bohr-phase evaluations of a stage; callers test the
+// argument range once for all phases of a stage (DP_TRIG_MAX).  Coefficients live in constant memory so that every
+// DFMA takes its constant straight from the bank (as 64-bit immediates each one cost two UMOV per use).
+#define DP_TRIG_MAX 1.0e5
+static __constant__ double DP_TRIG[16] = {6.36619772367581382433e-01, 1.5707963267948966, 6.123233995736766e-17, 0.0,
+                                   1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                   -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+                                   -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                                   2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+__device__ __forceinline__ void dp_sincos_fast(double x, double* sn, double* cs) {
+  const double n = rint(x * DP_TRIG[0]);
+  double r = fma(-n, DP_TRIG[1], x);
+  r = fma(-n, DP_TRIG[2], r);
+  const double z = r * r;
+  double ps = fma(z, DP_TRIG[4], DP_TRIG[5]);
+  ps = fma(z, ps, DP_TRIG[6]);
+  ps = fma(z, ps, DP_TRIG[7]);
+  ps = fma(z, ps, DP_TRIG[8]);
+  ps = fma(z, ps, DP_TRIG[9]);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, DP_TRIG[10], DP_TRIG[11]);
+  pc = fma(z, pc, DP_TRIG[12]);
+  pc = fma(z, pc, DP_TRIG[13]);
+  pc = fma(z, pc, DP_TRIG[14]);
+  pc = fma(z, pc, DP_TRIG[15]);
+  const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = (int)n;
+  const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+

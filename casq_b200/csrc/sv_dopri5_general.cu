@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "envelope.cuh"
+#include "dopri5_common.cuh"
 
 #define DG_MAXK 4
 #define DG_WARPS 4
@@ -27,9 +28,10 @@ struct DopriGenArgs {
   double* out;
   long long* nsteps;
   int* status;
-  DevSlots slots;
+  const double2* env_tab;  // [KA][n_total][B] envelope samples (casq_env_table_kernel)
   int n_total;
-  double dt_sample, rtol, atol, hmax;
+  double dt_sample, inv_dt_sample, rtol, atol, hmax;
+  double max_abs_freq;  // largest |carrier or frame frequency| (rad/s): decides the branch-free sincos per call
   long long mxstep;
   double two_pi_nu[DG_MAXK];
   const double* fe;       // [d] frame eigenvalues
@@ -40,20 +42,6 @@ struct DopriGenArgs {
   int identityU;
   const double2* U;       // [d][d]
 };
-
-__device__ __forceinline__ int dg_sample_index(double t, double dt, int n_total) {
-  double mod = fmod(t, dt);
-  double div = (t - mod) / dt;
-  if (mod != 0.0 && (mod < 0)) div -= 1.0;
-  double fl = 0.0;
-  if (div != 0.0) {
-    fl = floor(div);
-    if (div - fl > 0.5) fl += 1.0;
-  }
-  if (fl < -1.0) fl = -1.0;
-  if (fl > (double)n_total) fl = (double)n_total;
-  return (int)fl;
-}
 
 __device__ __forceinline__ double dg_warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -105,27 +93,26 @@ __global__ void __launch_bounds__(32 * DG_WARPS) sv_dopri5_general_kernel(const 
     fe[r] = own[r] ? a.fe[lane + 32 * r] : 0.0;
   }
 
-  int cur_idx = -2;
-  dcplx env[DG_MAXK];
-#pragma unroll
-  for (int k = 0; k < DG_MAXK; k++) env[k].re = env[k].im = 0.0;
-
   // k = -i p (A (conj(p) v)) at time t
   auto rhs = [&](double t, const double* vr, const double* vi, double* kr, double* ki) {
-    const int gidx = dg_sample_index(t, a.dt_sample, a.n_total);
-    if (gidx != cur_idx) {  // warp-uniform
-      cur_idx = gidx;
-      casq_channel_envelopes<DG_MAXK>(a.slots, a.params, a.B, b, gidx, env);
-    }
+    // envelope samples from the per-solve table (casq_env_table_kernel); phases below |x| = 1e5 with the branch-free
+    // sincos (one warp-uniform range test per call: t is the same for all lanes)
+    const int gidx = dev_sample_index_fast(t, a.dt_sample, a.inv_dt_sample, a.n_total);
+    const bool inside = gidx >= 0 && gidx < a.n_total;
+    const bool fast_trig = a.max_abs_freq * fabs(t) < DP_TRIG_MAX;
     double zr[DG_MAXK], zi[DG_MAXK];
 #pragma unroll
     for (int k = 0; k < DG_MAXK; k++) {
       zr[k] = zi[k] = 0.0;
-      if (k < KA) {
+      if (k < KA && inside) {
+        const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
         double s, c;
-        sincos(a.two_pi_nu[k] * t, &s, &c);
-        zr[k] = env[k].re * c - env[k].im * s;
-        zi[k] = env[k].re * s + env[k].im * c;
+        if (fast_trig)
+          dp_sincos_fast(a.two_pi_nu[k] * t, &s, &c);
+        else
+          sincos(a.two_pi_nu[k] * t, &s, &c);
+        zr[k] = env.x * c - env.y * s;
+        zi[k] = env.x * s + env.y * c;
       }
     }
     double pr[R], pi[R];
@@ -135,7 +122,10 @@ __global__ void __launch_bounds__(32 * DG_WARPS) sv_dopri5_general_kernel(const 
       pr[r] = 1.0;
       pi[r] = 0.0;
       if (own[r]) {
-        sincos(fe[r] * t, &pi[r], &pr[r]);
+        if (fast_trig)
+          dp_sincos_fast(fe[r] * t, &pi[r], &pr[r]);
+        else
+          sincos(fe[r] * t, &pi[r], &pr[r]);
         zb[lane + 32 * r] = make_double2(pr[r] * vr[r] + pi[r] * vi[r], pr[r] * vi[r] - pi[r] * vr[r]);
       }
     }
@@ -478,14 +468,18 @@ int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots
   a.out = out_dev;
   a.nsteps = nsteps_dev;
   a.status = status_dev;
-  a.slots = slots;
   a.n_total = n_total;
   a.dt_sample = m->dt;
+  a.inv_dt_sample = 1.0 / m->dt;
   a.rtol = rtol;
   a.atol = atol;
   a.hmax = hmax;
   a.mxstep = mxstep;
-  for (int k = 0; k < KA; k++) a.two_pi_nu[k] = 2.0 * M_PI * m->nu[active[k]];
+  for (int k = 0; k < KA; k++) {
+    a.two_pi_nu[k] = 2.0 * M_PI * m->nu[active[k]];
+    a.max_abs_freq = std::max(a.max_abs_freq, std::fabs(a.two_pi_nu[k]));
+  }
+  for (int i = 0; i < d; i++) a.max_abs_freq = std::max(a.max_abs_freq, std::fabs(m->fe[i]));
   a.fe = (const double*)m->work0.p;
   a.ell_col = (const int*)ell;
   a.ell_S = (const double2*)(ell + off_S);
@@ -493,16 +487,29 @@ int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots
   a.ell_N = a.ell_P + (size_t)KA * ne;
   a.identityU = m->U_is_identity ? 1 : 0;
   a.U = (const double2*)m->work2.p;
-  const unsigned grid = (unsigned)((B + DG_WARPS - 1) / DG_WARPS);
 #define DG_LAUNCH(R_, RWA_)                                                                                                   \
   {                                                                                                                           \
     CASQ_CUDA(cudaFuncSetAttribute(sv_dopri5_general_kernel<R_, RWA_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     sv_dopri5_general_kernel<R_, RWA_><<<grid, 32 * DG_WARPS, smem, st>>>(a);                                                 \
   }
-  if (R == 1 && m->rwa) DG_LAUNCH(1, true)
-  else if (R == 1) DG_LAUNCH(1, false)
-  else if (m->rwa) DG_LAUNCH(2, true)
-  else DG_LAUNCH(2, false)
+  // the batch is walked in windows that bound the envelope table
+  const long long Bw = casq_env_table_window(KA, n_total, B);
+  if ((rc = m->work3.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
+  a.env_tab = (const double2*)m->work3.p;
+  for (long long b0 = 0; b0 < B; b0 += Bw) {
+    const long long Bc = std::min(Bw, (long long)B - b0);
+    CASQ_CUDA(casq_launch_env_table<DG_MAXK>(KA, slots, params_dev, B, b0, Bc, n_total, (double2*)m->work3.p, st));
+    a.B = Bc;
+    a.y0 = y0_dev + (y0_batched ? b0 * 2 * d : 0);
+    a.out = out_dev + b0 * (long long)T_out * 2 * d;
+    a.nsteps = nsteps_dev ? nsteps_dev + 2 * b0 : nullptr;
+    a.status = status_dev ? status_dev + b0 : nullptr;
+    const unsigned grid = (unsigned)((Bc + DG_WARPS - 1) / DG_WARPS);
+    if (R == 1 && m->rwa) DG_LAUNCH(1, true)
+    else if (R == 1) DG_LAUNCH(1, false)
+    else if (m->rwa) DG_LAUNCH(2, true)
+    else DG_LAUNCH(2, false)
+  }
 #undef DG_LAUNCH
   CASQ_CUDA(cudaGetLastError());
   return CASQ_OK;

@@ -100,7 +100,7 @@ def test_max_slots_and_two_channels_d3(q0):
 
 
 def test_envelope_table_windows_give_identical_results(monkeypatch):
-    """Dopri5 (d <= 4) and the propagator path look the envelope up in a per-solve table that is built for windows of
+    """Dopri5 (both kernels) and the propagator path look the envelope up in a per-solve table that is built for windows of
     the batch (bounded memory for huge sweeps).  Forcing 3-point windows must not change a single bit."""
     st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
     nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
@@ -110,10 +110,20 @@ def test_envelope_table_windows_give_identical_results(monkeypatch):
     pk = engine.pack_params([p], device="cuda")
     y0 = np.array([1, 0, 0])
 
+    v = O.MANILA["vars"]
+    hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])},
+                                     {(0, 1): v["jq0q1"]})
+    st2, ops2, ch2, _ = O.parse_hamiltonian_dict(hd, None)
+    nm2 = NativeModel(st2, ops2, [O.MANILA_CARRIERS[c] for c in ch2], DT, rotating_frame=st2)  # d = 9: warp-per-trajectory Dopri5
+    y02 = np.zeros(9, dtype=complex)
+    y02[0] = 1
+
     def run():
         y, ns, stt = engine.solve_sv_dopri5(nm, [("drag", 0, 0, dur)], pk, y0, (0.0, dur * DT), rtol=1e-8, atol=1e-8, return_stats=True)
         U = engine.propagators_expm(nm, [("drag", 0, 0, dur)], pk, (0.0, dur * DT), DT / 2)
-        return y.clone(), ns.clone(), stt.clone(), U.clone()
+        y2, ns2, _ = engine.solve_sv_dopri5(nm2, [("drag", ch2.index("d0"), 0, dur)], pk, y02, (0.0, dur * DT), rtol=1e-8, atol=1e-8,
+                                            return_stats=True)
+        return y.clone(), ns.clone(), stt.clone(), U.clone(), y2.clone(), ns2.clone()
 
     monkeypatch.delenv("CASQ_ENV_TABLE_MAX_KB", raising=False)
     ref = run()
