@@ -63,7 +63,8 @@ def main():
                              "accepted_steps_total": int(ns5[:, 1].sum()), "failed": int((st5 != 0).sum()),
                              "best_infidelity_1_minus_P1fold": float((1 - pops[:, -1, 1]).min()),
                              "best_infidelity_true_1_minus_psi1sq": float((1 - probs[:, -1, 1]).min()),
-                             "flop_per_attempted_step": 1152}
+                             "flop_per_attempted_step": 1152,
+                             "algorithmic_TFLOPs": int(ns5[:, 0].sum()) * 1152 / (best * 1e-3) / 1e12}
     # ---- cfg 3: 2 transmons, GaussianSquare on u0, 64x64 sweep, expm-midpoint, RWA m=1 and no-RWA m=20
     v = O.MANILA["vars"]
     hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])}, {(0, 1): v["jq0q1"]})
@@ -81,7 +82,9 @@ def main():
         U = keep["U"]
         unit = float((U.conj().transpose(1, 2) @ U - torch.eye(9, device="cuda", dtype=U.dtype)).abs().max())
         res[f"cfg3_expm_d9_{tag}"] = {"B": 4096, "steps": 1024 * sub, "ms_best": best, "traj_per_s": 4096 / best * 1e3,
-                                      "max_unitarity_defect": unit, "rwa_cutoff_hz": rwa}
+                                      "max_unitarity_defect": unit, "rwa_cutoff_hz": rwa,
+                                      # F_expm(9, s=2) ~ 6.0e4 flop per step (Pade-13 count; the kernel executes orders 3-5)
+                                      "algorithmic_TFLOPs": 4096 * 1024 * sub * 6.0e4 / (best * 1e-3) / 1e12}
     # ---- cfg 4: 5 transmons d=243, Lindblad T1/T2, RWA, max_dt = dt/4, S = 1028, B = 128 per GPU
     st5m, ops5, ch5, _ = O.parse_hamiltonian_dict(O.MANILA, None)
     nm5 = NativeModel(st5m, ops5, [O.MANILA_CARRIERS[c] for c in ch5], DT, rotating_frame=np.diag(st5m).real, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"])
@@ -99,6 +102,26 @@ def main():
                                  "algorithmic_GBps": alg_bytes / (best * 1e-3) / 1e9, "hbm_peak_GBps_measured": 6554.6,
                                  "trace_min": float(pops.sum(-1).min()), "trace_max": float(pops.sum(-1).max()),
                                  "P_ground_first_last": [float(pops[0, 0]), float(pops[-1, 0])]}
+    # ---- beyond d = 4: lane-group RK4 and warp-per-trajectory Dopri5 on 2 and 3 coupled transmons (not BASELINE configs)
+    if not args.quick:
+        Bg = 4096
+        for nq in (2, 3):
+            qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(nq)}
+            cm = {(q, q + 1): v[f"jq{q}q{q+1}"] for q in range(nq - 1)}
+            stg, opsg, chg, _ = O.parse_hamiltonian_dict(O.transmon_hamiltonian_dict(qm, cm), None)
+            dg = stg.shape[0]
+            nmg = NativeModel(stg, opsg, [O.MANILA_CARRIERS[c] for c in chg], DT, rotating_frame=stg)
+            pg = engine.pack_params([dict(amp=rng.uniform(0.05, 0.5, Bg), angle=0.0, sigma=64.0, beta=rng.uniform(-2, 2, Bg))], device="cuda")
+            yg = np.zeros(dg, dtype=complex); yg[0] = 1
+            sl = [("drag", chg.index("d0"), 0, 256)]
+            best, _ = timed(lambda: engine.solve_sv_rk4(nmg, sl, pg, yg, (0, 257 * DT), DT / 40), reps=2, warm=1)
+            res[f"extra_rk4_general_d{dg}"] = {"B": Bg, "steps": 10280, "ms_best": best, "traj_per_s": Bg / best * 1e3}
+            outg = {}
+            def rung():
+                outg["r"] = engine.solve_sv_dopri5(nmg, sl, pg, yg, (0, 256 * DT), rtol=1e-8, atol=1e-6, hmax=DT, return_stats=True)
+            best, _ = timed(rung, reps=2, warm=1)
+            res[f"extra_dopri5_general_d{dg}"] = {"B": Bg, "ms_best": best, "traj_per_s": Bg / best * 1e3,
+                                                  "attempted_steps_total": int(outg["r"][1][:, 0].sum()), "failed": int((outg["r"][2] != 0).sum())}
     txt = json.dumps(res, indent=1)
     print(txt)
     if args.out:
