@@ -1,5 +1,5 @@
 // casq_b200: piecewise-constant propagators U = prod_n expm(h G_F(t_n + h/2)) for batches of pulse points,
-// one warp per trajectory, all matrices in shared memory (dim <= 16).
+// one warp per trajectory, all matrices in shared memory (dim <= 32: 4 warps per block up to dim 16, 2 above).
 //
 // This is the exponential-midpoint scheme of qiskit-dynamics' fixed-step "scipy_expm"/"jax_expm" solvers
 // (SURVEY.md Appendix A.5 last bullet).  casq's ODESolverMethod enum cannot select them
@@ -17,7 +17,8 @@
 #include "envelope.cuh"
 
 #define PROP_MAXK 4
-#define PROP_WARPS 4
+#define PROP_WARPS 4   // warps per block for dim <= 16 (two for 16 < dim <= 32: 6 work matrices of dim^2 per warp)
+#define PROP_MAXD 32
 
 struct PropArgs {
   const double* table;  // [NT][W]: carriers then p_i at every stage time (midpoints are the odd entries)
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_e
   const int d = DT > 0 ? DT : a.d, KA = a.KA, n2 = d * d;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long b = (long long)blockIdx.x * PROP_WARPS + warp;
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= a.B) return;
   double2* ws = reinterpret_cast<double2*>(smem_raw) + (size_t)warp * PROP_NBUF * n2;
   double2 *A = ws, *Uacc = ws + n2, *X1 = ws + 2 * n2, *X2 = ws + 3 * n2, *X3 = ws + 4 * n2, *X4 = ws + 5 * n2;
@@ -420,8 +421,8 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
     KA = 1;
   }
   const int d = m->d;
-  if (d < 2 || d > 16 || KA > PROP_MAXK)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_propagators_expm: dim %d with %d active channels is outside the built kernel (dim <= 16)", d, KA);
+  if (d < 2 || d > PROP_MAXD || KA > PROP_MAXK)
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_propagators_expm: dim %d with %d active channels is outside the built kernel (dim <= 32)", d, KA);
   cudaStream_t st = (cudaStream_t)stream;
   CASQ_CUDA(cudaSetDevice(m->device));
   TimeGrid g;
@@ -483,7 +484,8 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
   a.N = a.P + (size_t)KA * n2;
   a.U = a.N + (size_t)KA * n2;
   a.identityU = m->U_is_identity ? 1 : 0;
-  const size_t smem = (size_t)PROP_WARPS * PROP_NBUF * n2 * sizeof(double2);
+  const int wpb = d <= 16 ? PROP_WARPS : 2;
+  const size_t smem = (size_t)wpb * PROP_NBUF * n2 * sizeof(double2);
   // the batch is walked in windows that bound the envelope table
   const long long Bw = casq_env_table_window(KA, n_total, B);
   if ((rc = m->work2.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
@@ -493,14 +495,14 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
 #define PROP_LAUNCH(DT_)                                                                                              \
   {                                                                                                                   \
     CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_kernel<DT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    propagator_expm_kernel<DT_><<<grid, 32 * PROP_WARPS, smem, st>>>(a);                                              \
+    propagator_expm_kernel<DT_><<<grid, 32 * wpb, smem, st>>>(a);                                                     \
   }
   for (long long b0 = 0; b0 < B; b0 += Bw) {
     const long long Bc = std::min(Bw, (long long)B - b0);
     CASQ_CUDA(casq_launch_env_table<PROP_MAXK>(KA, ds, params_dev, B, b0, Bc, n_total, (double2*)m->work2.p, st));
     a.B = Bc;
     a.out = out_dev + b0 * 2LL * n2;
-    const unsigned grid = (unsigned)((Bc + PROP_WARPS - 1) / PROP_WARPS);
+    const unsigned grid = (unsigned)((Bc + wpb - 1) / wpb);
     switch (d) {
       case 2: PROP_LAUNCH(2) break;
       case 3: PROP_LAUNCH(3) break;

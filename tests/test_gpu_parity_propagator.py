@@ -85,3 +85,25 @@ def test_propagators_match_oracle_d9_all_pade_orders(rwa):
         want = O.expm_midpoint_propagators(om, samples, (0.0, dur * DT), max_dt)
         got = engine.propagators_expm(nm, slots, engine.pack_params(ps, device="cuda"), (0.0, dur * DT), max_dt).cpu().numpy()
         assert np.abs(got - want).max() < TOL_U, (rwa, max_dt)
+
+
+def test_propagators_match_oracle_d27_three_transmons():
+    """dim 27 (three coupled transmons): the generic warp-per-trajectory kernel with two warps per block; unitaries of a
+    DRAG pulse on d1 against scipy's expm per step, with and without RWA, and an unsupported-size error above dim 32."""
+    rng = np.random.default_rng(21)
+    v = O.MANILA["vars"]
+    qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(3)}
+    hd = O.transmon_hamiltonian_dict(qm, {(0, 1): v["jq0q1"], (1, 2): v["jq1q2"]})
+    st, ops, ch, _ = O.parse_hamiltonian_dict(hd, None)
+    assert st.shape == (27, 27)
+    B, dur = 3, 6
+    p = dict(amp=rng.uniform(0.2, 0.9, B), angle=rng.uniform(-1, 1, B), sigma=2.0, beta=rng.uniform(-1, 1, B))
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d1", dur)], [p])
+    for rwa, max_dt in ((None, DT / 8), (3.0e9, DT), (None, 2 * DT)):
+        om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st, rwa_cutoff_freq=rwa)
+        nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st, rwa_cutoff_freq=rwa)
+        want = O.expm_midpoint_propagators(om, samples, (0.0, dur * DT), max_dt)
+        got = engine.propagators_expm(nm, [("drag", ch.index("d1"), 0, dur)], engine.pack_params([p], device="cuda"), (0.0, dur * DT),
+                                      max_dt).cpu().numpy()
+        assert got.shape == (B, 27, 27) and np.abs(got - want).max() < TOL_U, (rwa, max_dt)
+        assert max(np.abs(u.conj().T @ u - np.eye(27)).max() for u in got) < 1e-11
