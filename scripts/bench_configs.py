@@ -5,11 +5,11 @@ Usage: python scripts/bench_configs.py [--out FILE] [--quick]"""
 import argparse, json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle as O
 from casq_b200 import engine
-from casq_b200._native import NativeModel
+from scripts import _problems as P
+from scripts._problems import t1t2  # noqa: F401  (re-exported for the other scripts)
 
-DT = O.MANILA_DT
+DT = P.DT
 
 
 def timed(fn, reps=3, warm=1):
@@ -24,27 +24,14 @@ def timed(fn, reps=3, warm=1):
     return min(ts), sum(ts) / len(ts)
 
 
-def t1t2(nq, T1=100e-6, T2=80e-6):
-    a = np.diag(np.sqrt(np.arange(1, 3)), k=1).astype(complex); n = a.conj().T @ a
-    out = []
-    for q in range(nq):
-        def emb(m_):
-            full = np.array([[1.0 + 0j]])
-            for s in range(nq):
-                full = np.kron(m_ if s == q else np.eye(3), full)
-            return full
-        out += [np.sqrt(1 / T1) * emb(a), np.sqrt(2 * (1 / T2 - 1 / (2 * T1))) * emb(n)]
-    return np.array(out)
-
-
 def main():
     ap = argparse.ArgumentParser(); ap.add_argument("--out", default=None); ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     res = {"gpu": torch.cuda.get_device_name(0), "fp64_fma_probe_tflops": engine.fp64_fma_probe()}
     rng = np.random.default_rng(20260101)
     # ---- cfg 2
-    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
-    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
+    st, ops, ch = P.manila([0])
+    nm = P.native(st, ops, ch)
     bb, aa = np.meshgrid(np.linspace(-5, 5, 250), np.linspace(0.02, 0.5, 400), indexing="ij")
     p = engine.pack_params([dict(amp=aa.ravel(), angle=0.0, sigma=64.0, beta=bb.ravel())], device="cuda")
     y0 = np.array([1, 0, 0])
@@ -66,15 +53,13 @@ def main():
                              "flop_per_attempted_step": 1152,
                              "algorithmic_TFLOPs": int(ns5[:, 0].sum()) * 1152 / (best * 1e-3) / 1e12}
     # ---- cfg 3: 2 transmons, GaussianSquare on u0, 64x64 sweep, expm-midpoint, RWA m=1 and no-RWA m=20
-    v = O.MANILA["vars"]
-    hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])}, {(0, 1): v["jq0q1"]})
-    st2, ops2, ch2, _ = O.parse_hamiltonian_dict(hd, None)
+    st2, ops2, ch2 = P.chain(2)
     ww, aa3 = np.meshgrid(np.linspace(0, 768, 64), np.linspace(0.05, 0.8, 64), indexing="ij")
     p3 = engine.pack_params([dict(amp=aa3.ravel(), angle=0.0, sigma=64.0, width=ww.ravel())], device="cuda")
-    for tag, rwa, sub in (("rwa_m1", 0.75 * O.MANILA_CARRIERS["d0"], 1), ("norwa_m20", None, 20)):
+    for tag, rwa, sub in (("rwa_m1", 0.75 * P.CARRIERS["d0"], 1), ("norwa_m20", None, 20)):
         if args.quick and sub == 20:
             continue
-        nm2 = NativeModel(st2, ops2, [O.MANILA_CARRIERS[c] for c in ch2], DT, rotating_frame=st2, rwa_cutoff_freq=rwa)
+        nm2 = P.native(st2, ops2, ch2, rwa=rwa)
         keep = {}
         def run3():
             keep["U"] = engine.propagators_expm(nm2, [("gaussian_square", ch2.index("u0"), 0, 1024)], p3, (0, 1024 * DT), DT / sub)
@@ -86,8 +71,8 @@ def main():
                                       # F_expm(9, s=2) ~ 6.0e4 flop per step (Pade-13 count; the kernel executes orders 3-5)
                                       "algorithmic_TFLOPs": 4096 * 1024 * sub * 6.0e4 / (best * 1e-3) / 1e12}
     # ---- cfg 4: 5 transmons d=243, Lindblad T1/T2, RWA, max_dt = dt/4, S = 1028, B = 128 per GPU
-    st5m, ops5, ch5, _ = O.parse_hamiltonian_dict(O.MANILA, None)
-    nm5 = NativeModel(st5m, ops5, [O.MANILA_CARRIERS[c] for c in ch5], DT, rotating_frame=np.diag(st5m).real, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"])
+    st5m, ops5, ch5 = P.manila(None)
+    nm5 = P.native(st5m, ops5, ch5, frame="diag", rwa=0.75 * P.CARRIERS["d0"])
     nm5.set_dissipators(t1t2(5))
     B4 = 16 if args.quick else 128
     p4 = engine.pack_params([dict(amp=np.linspace(0.05, 0.5, B4), angle=0.0, sigma=64.0, beta=1.0)], device="cuda")
@@ -106,11 +91,9 @@ def main():
     if not args.quick:
         Bg = 4096
         for nq in (2, 3):
-            qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(nq)}
-            cm = {(q, q + 1): v[f"jq{q}q{q+1}"] for q in range(nq - 1)}
-            stg, opsg, chg, _ = O.parse_hamiltonian_dict(O.transmon_hamiltonian_dict(qm, cm), None)
+            stg, opsg, chg = P.chain(nq)
             dg = stg.shape[0]
-            nmg = NativeModel(stg, opsg, [O.MANILA_CARRIERS[c] for c in chg], DT, rotating_frame=stg)
+            nmg = P.native(stg, opsg, chg)
             pg = engine.pack_params([dict(amp=rng.uniform(0.05, 0.5, Bg), angle=0.0, sigma=64.0, beta=rng.uniform(-2, 2, Bg))], device="cuda")
             yg = np.zeros(dg, dtype=complex); yg[0] = 1
             sl = [("drag", chg.index("d0"), 0, 256)]

@@ -12,13 +12,11 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-import oracle as O  # problem definitions only (constants, Hamiltonian strings): nothing of the oracle is timed
 from casq_b200 import engine
-from casq_b200._native import NativeModel
 from casq_b200.distributed import gather_batch, shard_bounds
-from scripts.bench_configs import t1t2
+from scripts import _problems as P
 
-DT = O.MANILA_DT
+DT = P.DT
 
 
 def timed_ranks(fn, reps, warm):
@@ -45,10 +43,9 @@ def main():
     res = {"n_gpus": world, "gpu": torch.cuda.get_device_name(local)}
 
     # ---- cfg 4: 5 transmons, T1/T2, DRAG on d0, RK4 dt/4 with RWA, 128 density matrices per GPU
-    st5, ops5, ch5, _ = O.parse_hamiltonian_dict(O.MANILA, None)
-    nm5 = NativeModel(st5, ops5, [O.MANILA_CARRIERS[c] for c in ch5], DT, rotating_frame=np.diag(st5).real,
-                      rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"], device=local)
-    nm5.set_dissipators(t1t2(5))
+    st5, ops5, ch5 = P.manila(None)
+    nm5 = P.native(st5, ops5, ch5, frame="diag", rwa=0.75 * P.CARRIERS["d0"], device=local)
+    nm5.set_dissipators(P.t1t2(5))
     B4 = 128 * world
     lo, hi = shard_bounds(B4, rank, world)
     amp = np.linspace(0.05, 0.5, B4)[lo:hi]
@@ -67,10 +64,8 @@ def main():
                                      "trace_max": float(pops[:, -1].sum(-1).max())}
 
     # ---- cfg 3: 4096 cross-resonance unitaries per GPU
-    v = O.MANILA["vars"]
-    hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])}, {(0, 1): v["jq0q1"]})
-    st2, ops2, ch2, _ = O.parse_hamiltonian_dict(hd, None)
-    nm2 = NativeModel(st2, ops2, [O.MANILA_CARRIERS[c] for c in ch2], DT, rotating_frame=st2, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"], device=local)
+    st2, ops2, ch2 = P.chain(2)
+    nm2 = P.native(st2, ops2, ch2, rwa=0.75 * P.CARRIERS["d0"], device=local)
     B3 = 4096 * world
     ww, aa = np.meshgrid(np.linspace(0, 768, 64 * world), np.linspace(0.05, 0.8, 64), indexing="ij")
     lo, hi = shard_bounds(B3, rank, world)
@@ -83,8 +78,8 @@ def main():
         res["cfg3_expm_d9_rwa_m1"] = {"B_total": B3, "ms_best": ms, "traj_per_s": B3 / ms * 1e3, "gathered_shape": list(keep["U"].shape)}
 
     # ---- cfg 5: 1e4 Dopri5 candidates per GPU
-    st1, ops1, ch1, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
-    nm1 = NativeModel(st1, ops1, [O.MANILA_CARRIERS[c] for c in ch1], DT, rotating_frame=st1, device=local)
+    st1, ops1, ch1 = P.manila([0])
+    nm1 = P.native(st1, ops1, ch1, device=local)
     B5 = 10000 * world
     rng = np.random.default_rng(20260101)
     sig, bet = rng.uniform(16, 128, B5), rng.uniform(-4, 4, B5)

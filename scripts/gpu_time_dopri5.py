@@ -1,14 +1,14 @@
 """BASELINE cfg 5 alone: 1e4 DRAG candidates, adaptive Dopri5 (atol 1e-6, rtol 1e-8, hmax dt).  Usage: gpu_time_dopri5.py [B]"""
 import sys; sys.path.insert(0, ".")
-import numpy as np, torch, oracle as O
+import numpy as np, torch
 from casq_b200 import engine
-from casq_b200._native import NativeModel
+from scripts import _problems as P
 from scripts.bench_configs import timed
-DT = O.MANILA_DT
+DT = P.DT
 B5 = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 rng = np.random.default_rng(20260101)
-st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
-nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
+st, ops, ch = P.manila([0])
+nm = P.native(st, ops, ch)
 p5 = engine.pack_params([dict(amp=0.12, angle=0.0, sigma=rng.uniform(16, 128, B5), beta=rng.uniform(-4, 4, B5))], device="cuda")
 out5 = {}
 def run5():

@@ -1,16 +1,15 @@
+"""BASELINE cfg 3 alone: NSxNS cross-resonance GaussianSquare unitaries (d = 9), expm-midpoint, RWA.  Usage: gpu_time_expm.py [NS]"""
 import sys; sys.path.insert(0, ".")
-import numpy as np, torch, oracle as O
+import numpy as np, torch
 from casq_b200 import engine
-from casq_b200._native import NativeModel
+from scripts import _problems as P
 from scripts.bench_configs import timed
-DT = O.MANILA_DT
-v = O.MANILA["vars"]
-hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])}, {(0, 1): v["jq0q1"]})
-st2, ops2, ch2, _ = O.parse_hamiltonian_dict(hd, None)
+DT = P.DT
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+st2, ops2, ch2 = P.chain(2)
 ww, aa3 = np.meshgrid(np.linspace(0, 768, NS), np.linspace(0.05, 0.8, NS), indexing="ij")
 p3 = engine.pack_params([dict(amp=aa3.ravel(), angle=0.0, sigma=64.0, width=ww.ravel())], device="cuda")
-nm2 = NativeModel(st2, ops2, [O.MANILA_CARRIERS[c] for c in ch2], DT, rotating_frame=st2, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"])
+nm2 = P.native(st2, ops2, ch2, rwa=0.75 * P.CARRIERS["d0"])
 keep = {}
 def run3():
     keep["U"] = engine.propagators_expm(nm2, [("gaussian_square", ch2.index("u0"), 0, 1024)], p3, (0, 1024 * DT), DT)

@@ -1,20 +1,17 @@
 """State-vector steppers beyond d = 4 (lane-group RK4 and warp-per-trajectory Dopri5): two and three coupled transmons.
 Usage: gpu_time_general.py [B]"""
 import sys; sys.path.insert(0, ".")
-import numpy as np, torch, oracle as O
+import numpy as np, torch
 from casq_b200 import engine
-from casq_b200._native import NativeModel
+from scripts import _problems as P
 from scripts.bench_configs import timed
-DT = O.MANILA_DT
+DT = P.DT
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-v = O.MANILA["vars"]
 rng = np.random.default_rng(20260101)
 for nq in (2, 3):
-    qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(nq)}
-    cm = {(q, q + 1): v[f"jq{q}q{q+1}"] for q in range(nq - 1)}
-    st, ops, ch, _ = O.parse_hamiltonian_dict(O.transmon_hamiltonian_dict(qm, cm), None)
+    st, ops, ch = P.chain(nq)
     d = st.shape[0]
-    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
+    nm = P.native(st, ops, ch)
     p = engine.pack_params([dict(amp=rng.uniform(0.05, 0.5, B), angle=0.0, sigma=64.0, beta=rng.uniform(-2, 2, B))], device="cuda")
     y0 = np.zeros(d, dtype=complex); y0[0] = 1
     slots = [("drag", ch.index("d0"), 0, 256)]

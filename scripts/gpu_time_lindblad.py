@@ -1,12 +1,13 @@
-import sys, os; sys.path.insert(0, ".")
-import numpy as np, torch, oracle as O
+"""BASELINE cfg 4 alone: 5 transmons (d = 243), T1/T2, DRAG on d0, RK4 dt/4 with RWA.  Usage: gpu_time_lindblad.py [B]"""
+import sys; sys.path.insert(0, ".")
+import numpy as np, torch
 from casq_b200 import engine
-from casq_b200._native import NativeModel
-from scripts.bench_configs import t1t2, timed
-DT = O.MANILA_DT
-st5m, ops5, ch5, _ = O.parse_hamiltonian_dict(O.MANILA, None)
-nm5 = NativeModel(st5m, ops5, [O.MANILA_CARRIERS[c] for c in ch5], DT, rotating_frame=np.diag(st5m).real, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"])
-nm5.set_dissipators(t1t2(5))
+from scripts import _problems as P
+from scripts.bench_configs import timed
+DT = P.DT
+st5, ops5, ch5 = P.manila(None)
+nm5 = P.native(st5, ops5, ch5, frame="diag", rwa=0.75 * P.CARRIERS["d0"])
+nm5.set_dissipators(P.t1t2(5))
 B4 = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 p4 = engine.pack_params([dict(amp=np.linspace(0.05, 0.5, B4), angle=0.0, sigma=64.0, beta=1.0)], device="cuda")
 rho0 = np.zeros(243, dtype=complex); rho0[0] = 1
