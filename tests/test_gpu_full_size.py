@@ -1,4 +1,4 @@
-"""BASELINE.json configs 3-5 at FULL size on the GPU, checked through size-independent properties (the oracle
+"""BASELINE.json configs 1 and 3-5 at FULL size on the GPU, checked through size-independent properties (the oracle
 needs hours at these sizes): unitarity, norm / trace conservation, positivity, linearity, and oracle spot checks
 on a handful of points.  cfg 2 at full size lives in tests/test_gpu_parity_sv.py::test_rk4_full_size_properties."""
 import numpy as np
@@ -116,3 +116,33 @@ def test_cfg4_full_size_lindblad_manila():
     # couplings J ~ 2 MHz act for 57 ns: the marginal of qubit 0 differs from the isolated qubit at the 1e-3 level
     marg = pp.cpu().numpy().reshape(B, 81, 3).sum(1)
     assert np.abs(marg - p_single).max() < 5e-3
+
+
+def test_cfg1_full_size_gaussian_rabi_sweep():
+    """BASELINE cfg 1 at full size: GaussianPulseGate(duration=256, sigma=64), a = linspace(0, 1, 101) on the 3-level
+    ibmq_manila qubit 0, t in [0, 257 dt].  The reference runs SCIPY_DOP853 at 1e-12; here the adaptive Dopri5 at 1e-12
+    is the tight solve and the fixed-step RK4 (dt/40) must agree with it to its own sampled-envelope accuracy.
+    Known answer: the first pi pulse sits at a ~ 0.1109, so on this grid P("1") peaks at a = 0.11."""
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=st)
+    amp = np.linspace(0, 1, 101)
+    p = engine.pack_params([dict(amp=amp, angle=0.0, sigma=64.0)], device="cuda")
+    slots = [("gaussian", 0, 0, 256)]
+    span = (0.0, 257 * DT)
+    y0 = np.array([1, 0, 0])
+    tight, ns, status = engine.solve_sv_dopri5(nm, slots, p, y0, span, rtol=1e-12, atol=1e-12, return_stats=True)
+    assert int(status.abs().sum()) == 0
+    rk4 = engine.solve_sv_rk4(nm, slots, p, y0, span, DT / 40)
+    assert float((tight[:, -1] - rk4[:, -1]).abs().max()) < 5e-4  # RK4 is first order at sample boundaries (DESIGN 6)
+    assert float((torch.linalg.vector_norm(tight[:, -1], dim=1) - 1).abs().max()) < 1e-9
+    _, probs, pops = engine.postprocess_sv(nm, np.array(span), tight)
+    p1 = pops[:, -1, 1].cpu().numpy()  # levels > 1 folded into "1" (casq's populations)
+    true_p1 = probs[:, -1, 1].cpu().numpy()
+    assert p1[0] < 1e-12 and abs(float(amp[np.argmax(true_p1[:20])]) - 0.11) < 1e-12
+    assert true_p1[11] > 0.999  # a = 0.11 is within 1 % of the pi-pulse amplitude
+    # oracle spot check on three amplitudes with the same solver settings
+    idx = np.array([11, 50, 100])
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st)
+    samples = O.channel_samples(ch, [O.PulseSpec("gaussian", "d0", 256)], [dict(amp=amp[idx], angle=0.0, sigma=64.0)])
+    _, want = O.dop853_solve(om, samples, y0, span)
+    assert np.abs(tight.cpu().numpy()[idx, -1] - want[:, -1]).max() < 1e-7
