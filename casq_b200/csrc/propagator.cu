@@ -1,5 +1,6 @@
 // casq_b200: piecewise-constant propagators U = prod_n expm(h G_F(t_n + h/2)) for batches of pulse points,
-// one warp per trajectory, all matrices in shared memory (dim <= 32: 4 warps per block up to dim 16, 2 above).
+// one warp per trajectory, all matrices in shared memory, for dim <= 16; a block per trajectory (propagator_block.cuh)
+// for 16 < dim <= 32.
 //
 // This is the exponential-midpoint scheme of qiskit-dynamics' fixed-step "scipy_expm"/"jax_expm" solvers
 // (SURVEY.md Appendix A.5 last bullet).  casq's ODESolverMethod enum cannot select them
@@ -17,7 +18,7 @@
 #include "envelope.cuh"
 
 #define PROP_MAXK 4
-#define PROP_WARPS 4   // warps per block for dim <= 16 (two for 16 < dim <= 32: 6 work matrices of dim^2 per warp)
+#define PROP_WARPS 4   // warps (= trajectories) per block of the warp-per-trajectory kernel
 #define PROP_MAXD 32
 
 struct PropArgs {
@@ -397,6 +398,8 @@ __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_e
   }
 }
 
+#include "propagator_block.cuh"
+
 __global__ void sv_general_table_kernel(const double* __restrict__ times, long long NT, int KA, int d, int W,
                                         const double* __restrict__ two_pi_nu, const double* __restrict__ fe,
                                         double* __restrict__ out);
@@ -502,6 +505,19 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
     CASQ_CUDA(casq_launch_env_table<PROP_MAXK>(KA, ds, params_dev, B, b0, Bc, n_total, (double2*)m->work2.p, st));
     a.B = Bc;
     a.out = out_dev + b0 * 2LL * n2;
+    if (d > 16) {  // a block per trajectory (propagator_block.cuh)
+      const size_t smem_b = (size_t)PROP_NBUF * n2 * sizeof(double2);
+#define PROP_BLOCK_LAUNCH(TS_)                                                                                                    \
+  {                                                                                                                               \
+    CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_block_kernel<TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); \
+    propagator_expm_block_kernel<TS_><<<(unsigned)Bc, PB_THREADS, smem_b, st>>>(a);                                               \
+  }
+      if (d % 3 == 0) PROP_BLOCK_LAUNCH(3)
+      else if (d % 2 == 0) PROP_BLOCK_LAUNCH(2)
+      else PROP_BLOCK_LAUNCH(1)
+#undef PROP_BLOCK_LAUNCH
+      continue;
+    }
     const unsigned grid = (unsigned)((Bc + wpb - 1) / wpb);
     switch (d) {
       case 2: PROP_LAUNCH(2) break;

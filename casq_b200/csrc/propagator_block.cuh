@@ -1,0 +1,281 @@
+// casq_b200: propagators for 16 < dim <= 32 (three coupled transmons: dim 27), ONE BLOCK of 128 threads per trajectory.
+//
+// Six dim x dim work matrices are 70 kB at dim 27: with a warp per trajectory only two warps fit an SM and every
+// lane walks 23 matrix elements per product (the generic kernel: 1.0e3 unitaries/s at dim 27).  Here the 128 threads
+// of a block share one trajectory: products are register tiled (a thread owns a TS x TS output tile, TS = 3 when
+// 3 | dim, else 2 or 1: per k it loads 2 TS operands for TS^2 complex FMAs), the Gauss-Jordan elimination and all
+// element-wise passes are strided over the block, and three blocks (12 warps) are resident per SM.
+// Same algorithm as propagator.cu (orders 3/5/7/9 by Higham's theta_m, scaling above theta_9, partial pivoting).
+#pragma once
+
+#define PB_THREADS 128
+
+// C = X * Y (d x d), block-cooperative; C must not alias X or Y.
+template <int TS>
+__device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double2* X, const double2* Y) {
+  const int nt = d / TS, ntiles = nt * nt;
+  for (int tile = tid; tile < ntiles; tile += PB_THREADS) {
+    const int ti = tile / nt, r0 = ti * TS, c0 = (tile - ti * nt) * TS;
+    double2 acc[TS][TS];
+#pragma unroll
+    for (int i = 0; i < TS; i++)
+#pragma unroll
+      for (int j = 0; j < TS; j++) acc[i][j] = make_double2(0.0, 0.0);
+    for (int k = 0; k < d; k++) {
+      double2 x[TS], y[TS];
+#pragma unroll
+      for (int i = 0; i < TS; i++) x[i] = X[(r0 + i) * d + k];
+#pragma unroll
+      for (int j = 0; j < TS; j++) y[j] = Y[k * d + c0 + j];
+#pragma unroll
+      for (int i = 0; i < TS; i++)
+#pragma unroll
+        for (int j = 0; j < TS; j++) acc[i][j] = cfma(x[i], y[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TS; i++)
+#pragma unroll
+      for (int j = 0; j < TS; j++) C[(r0 + i) * d + c0 + j] = acc[i][j];
+  }
+  __syncthreads();
+}
+
+// Solve Q X = Pm in place (X overwrites Pm); Q is destroyed.  Gauss-Jordan with partial pivoting; d <= 32, so the
+// pivot search is one pass of warp 0 and the chosen row travels through s_piv.
+__device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, int* s_piv) {
+  for (int k = 0; k < d; k++) {
+    if (tid < 32) {
+      double best = -1.0;
+      int brow = k;
+      const int r = k + tid;
+      if (r < d) {
+        const double2 v = Q[r * d + k];
+        best = v.x * v.x + v.y * v.y;
+        brow = r;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int orow = __shfl_xor_sync(0xffffffffu, brow, o);
+        if (ob > best || (ob == best && orow < brow)) {
+          best = ob;
+          brow = orow;
+        }
+      }
+      if (tid == 0) *s_piv = brow;
+    }
+    __syncthreads();
+    const int brow = *s_piv;
+    if (brow != k) {
+      for (int j = tid; j < 2 * d; j += PB_THREADS) {
+        double2* M = (j < d) ? Q : Pm;
+        const int c = (j < d) ? j : j - d;
+        const double2 t = M[k * d + c];
+        M[k * d + c] = M[brow * d + c];
+        M[brow * d + c] = t;
+      }
+      __syncthreads();
+    }
+    const double2 piv = Q[k * d + k];
+    const double inv_n = 1.0 / (piv.x * piv.x + piv.y * piv.y);
+    const double2 pinv = make_double2(piv.x * inv_n, -piv.y * inv_n);
+    __syncthreads();  // every thread has read the pivot before the row is scaled
+    for (int j = tid; j < 2 * d; j += PB_THREADS) {
+      double2* M = (j < d) ? Q : Pm;
+      const int c = (j < d) ? j : j - d;
+      if (j >= d || c >= k) M[k * d + c] = cmul(M[k * d + c], pinv);
+    }
+    __syncthreads();
+    // eliminate column k from every other row; columns <= k of Q are dead (never written: the factors stay readable)
+    const int w = 2 * d - (k + 1);  // live columns per row: Q columns k+1.., all of P
+    for (int e = tid; e < d * w; e += PB_THREADS) {
+      const int r = e / w, j = e - r * w + (k + 1);
+      if (r == k) continue;
+      double2* M = (j < d) ? Q : Pm;
+      const int c = (j < d) ? j : j - d;
+      const double2 f = Q[r * d + k];
+      const double2 p = M[k * d + c];
+      const double2 v = M[r * d + c];
+      M[r * d + c] = make_double2(v.x - (f.x * p.x - f.y * p.y), v.y - (f.x * p.y + f.y * p.x));
+    }
+    __syncthreads();
+  }
+}
+
+// expm(A) with four work matrices; returns the buffer holding the result (X1 or X2).  See wexpm (propagator.cu).
+template <int TS>
+__device__ double2* bexpm(int d, int tid, double2* A, double2* X1, double2* X2, double2* X3, double2* X4, double* s_red, int* s_piv) {
+  const int n2 = d * d;
+  for (int e = tid; e < n2; e += PB_THREADS) X4[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
+  __syncthreads();
+  if (tid < 32) {  // ||A||_1: lane j sums column j (d <= 32), warp max
+    double s = 0.0;
+    if (tid < d)
+      for (int i = 0; i < d; i++) s += X4[i * d + tid].x;
+    for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (tid == 0) *s_red = s;
+  }
+  __syncthreads();
+  const double nrm = *s_red;
+  int m, s = 0;
+  if (nrm < 1.495585217958292e-2)
+    m = 3;
+  else if (nrm < 2.539398330063230e-1)
+    m = 5;
+  else if (nrm < 9.504178996162932e-1)
+    m = 7;
+  else {
+    m = 9;
+    const double r = nrm / 2.097847961257068e0;
+    s = r > 1.0 ? (int)ceil(log2(r)) : 0;
+    if (s > 0) {
+      const double sc = ldexp(1.0, -s);
+      for (int e = tid; e < n2; e += PB_THREADS) A[e] = make_double2(A[e].x * sc, A[e].y * sc);
+    }
+  }
+  __syncthreads();  // also: every thread has read s_red / finished with the |A| scratch
+  double2 *A2 = X1, *A4 = X2, *A6 = X3, *A8 = X4, *Od = X4, *Vm = X3;
+  bmatmul<TS>(d, tid, A2, A, A);
+  auto diag = [&](int e) { return (e / d) == (e % d) ? 1.0 : 0.0; };
+  if (m == 3) {
+    const double b[4] = {120., 60., 12., 1.};
+    for (int e = tid; e < n2; e += PB_THREADS) {
+      Od[e] = make_double2(b[3] * A2[e].x + b[1] * diag(e), b[3] * A2[e].y);
+      Vm[e] = make_double2(b[2] * A2[e].x + b[0] * diag(e), b[2] * A2[e].y);
+    }
+  } else if (m == 5) {
+    const double b[6] = {30240., 15120., 3360., 420., 30., 1.};
+    bmatmul<TS>(d, tid, A4, A2, A2);
+    for (int e = tid; e < n2; e += PB_THREADS) {
+      Od[e] = make_double2(b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e), b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  } else if (m == 7) {
+    const double b[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+    bmatmul<TS>(d, tid, A4, A2, A2);
+    bmatmul<TS>(d, tid, A6, A4, A2);
+    for (int e = tid; e < n2; e += PB_THREADS) {  // V overwrites A^6 element by element
+      const double2 a6 = A6[e];
+      Od[e] = make_double2(b[7] * a6.x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e), b[7] * a6.y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[6] * a6.x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e), b[6] * a6.y + b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  } else {
+    const double b[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
+    bmatmul<TS>(d, tid, A4, A2, A2);
+    bmatmul<TS>(d, tid, A6, A4, A2);
+    bmatmul<TS>(d, tid, A8, A6, A2);
+    for (int e = tid; e < n2; e += PB_THREADS) {  // the polynomials overwrite A^8 and A^6 element by element
+      const double2 a8 = A8[e], a6 = A6[e];
+      Od[e] = make_double2(b[9] * a8.x + b[7] * a6.x + b[5] * A4[e].x + b[3] * A2[e].x + b[1] * diag(e),
+                           b[9] * a8.y + b[7] * a6.y + b[5] * A4[e].y + b[3] * A2[e].y);
+      Vm[e] = make_double2(b[8] * a8.x + b[6] * a6.x + b[4] * A4[e].x + b[2] * A2[e].x + b[0] * diag(e),
+                           b[8] * a8.y + b[6] * a6.y + b[4] * A4[e].y + b[2] * A2[e].y);
+    }
+  }
+  __syncthreads();
+  double2* Um = X1;  // A^2 is dead
+  bmatmul<TS>(d, tid, Um, A, Od);
+  for (int e = tid; e < n2; e += PB_THREADS) {  // Q = V - U (over V), P = V + U (over U)
+    const double2 v = Vm[e], u = Um[e];
+    X3[e] = make_double2(v.x - u.x, v.y - u.y);
+    X1[e] = make_double2(v.x + u.x, v.y + u.y);
+  }
+  __syncthreads();
+  bsolve(d, tid, X3, X1, s_piv);
+  double2 *E = X1, *Sq = X2;
+  for (int q = 0; q < s; q++) {
+    bmatmul<TS>(d, tid, Sq, E, E);
+    double2* t = E;
+    E = Sq;
+    Sq = t;
+  }
+  return E;
+}
+
+template <int TS>
+__global__ void __launch_bounds__(PB_THREADS) propagator_expm_block_kernel(const PropArgs a) {
+  const int d = a.d, KA = a.KA, n2 = d * d, tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red;
+  __shared__ int s_piv;
+  const long long b = blockIdx.x;
+  double2* ws = reinterpret_cast<double2*>(smem_raw);
+  double2 *A = ws, *Uacc = ws + n2, *X1 = ws + 2 * n2, *X2 = ws + 3 * n2, *X3 = ws + 4 * n2, *X4 = ws + 5 * n2;
+  for (int e = tid; e < n2; e += PB_THREADS) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
+  __syncthreads();
+
+  long long pos = 0;
+  for (int p = 0; p < a.n_pieces; p++) {
+    const int n = a.piece_n[p];
+    const double h = a.piece_h[p];
+    for (int s = 0; s < n; s++) {
+      const long long pm = pos + 1;  // midpoint entry
+      const int gidx = __ldg(a.idx + pm);
+      const bool inside = gidx >= 0 && gidx < a.n_total;
+      const double* ent = a.table + pm * a.W;
+      double zr[PROP_MAXK], zi[PROP_MAXK];
+#pragma unroll
+      for (int k = 0; k < PROP_MAXK; k++) {
+        zr[k] = zi[k] = 0.0;
+        if (k < KA && inside) {
+          const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
+          const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
+          zr[k] = env.x * c - env.y * sn;
+          zi[k] = env.x * sn + env.y * c;
+        }
+      }
+      const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
+      for (int e = tid; e < n2; e += PB_THREADS) {
+        const int i = e / d, j = e - i * d;
+        double2 m = __ldg(a.S + e);
+#pragma unroll
+        for (int k = 0; k < PROP_MAXK; k++) {
+          if (k < KA) {
+            const double2 P = __ldg(a.P + (size_t)k * n2 + e);
+            if (a.rwa) {
+              const double2 N = __ldg(a.N + (size_t)k * n2 + e);
+              m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
+              m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
+            } else {
+              m.x = fma(zr[k], P.x, m.x);
+              m.y = fma(zr[k], P.y, m.y);
+            }
+          }
+        }
+        const double2 pi_ = __ldg(ph + i), pj = __ldg(ph + j);
+        const double2 f = make_double2(pi_.x * pj.x + pi_.y * pj.y, pi_.y * pj.x - pi_.x * pj.y);  // p_i conj(p_j)
+        const double2 g = cmul(f, m);
+        A[e] = make_double2(h * g.y, -h * g.x);  // -i g
+      }
+      __syncthreads();
+      double2* E = bexpm<TS>(d, tid, A, X1, X2, X3, X4, &s_red, &s_piv);
+      bmatmul<TS>(d, tid, X4, E, Uacc);  // X4 is free once the odd polynomial has been consumed
+      double2* t = Uacc;
+      Uacc = X4;
+      X4 = t;
+      pos += 2;
+    }
+    pos += 1;
+  }
+  // out = V U V^+ (frame basis -> lab basis)
+  double2* o = reinterpret_cast<double2*>(a.out) + b * (long long)n2;
+  if (a.identityU) {
+    for (int e = tid; e < n2; e += PB_THREADS) o[e] = Uacc[e];
+  } else {
+    for (int e = tid; e < n2; e += PB_THREADS) {  // X1 = V U
+      const int i = e / d, j = e - i * d;
+      double2 acc = make_double2(0.0, 0.0);
+      for (int k = 0; k < d; k++) acc = cfma(__ldg(a.U + i * d + k), Uacc[k * d + j], acc);
+      X1[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < n2; e += PB_THREADS) {
+      const int i = e / d, j = e - i * d;
+      double2 acc = make_double2(0.0, 0.0);
+      for (int k = 0; k < d; k++) {
+        const double2 v = __ldg(a.U + j * d + k);
+        acc = cfma(X1[i * d + k], make_double2(v.x, -v.y), acc);
+      }
+      o[e] = acc;
+    }
+  }
+}
