@@ -1,39 +1,43 @@
-// casq_b200: propagators for 16 < dim <= 32 (three coupled transmons: dim 27), ONE BLOCK of 128 threads per trajectory.
+// casq_b200: propagators for 16 < dim <= 32 (three coupled transmons: dim 27), ONE BLOCK of 256 threads per trajectory.
 //
 // Six dim x dim work matrices are 70 kB at dim 27: with a warp per trajectory only two warps fit an SM and every
-// lane walks 23 matrix elements per product (the generic kernel: 1.0e3 unitaries/s at dim 27).  Here the 128 threads
+// lane walks 23 matrix elements per product (the generic kernel: 1.0e3 unitaries/s at dim 27).  Here the 256 threads
 // of a block share one trajectory: products are register tiled (a thread owns a TS x TS output tile, TS = 3 when
 // 3 | dim, else 2 or 1: per k it loads 2 TS operands for TS^2 complex FMAs), the Gauss-Jordan elimination and all
-// element-wise passes are strided over the block, and three blocks (12 warps) are resident per SM.
+// element-wise passes are strided over the block, and three blocks (24 warps) are resident per SM.
 // Same algorithm as propagator.cu (orders 3/5/7/9 by Higham's theta_m, scaling above theta_9, partial pivoting).
 #pragma once
 
-#define PB_THREADS 128
+#define PB_THREADS 256
 
-// C = X * Y (d x d), block-cooperative; C must not alias X or Y.
+// C = X * Y (d x d), block-cooperative; C must not alias X or Y.  A thread owns a TR x TS output tile.
+#ifndef PB_TILE_ROWS
+#define PB_TILE_ROWS(TS) (TS)  // square tiles: 1 x TS tiles put 3x the threads to work at dim 27 but ran 11 % slower (operand traffic)
+#endif
 template <int TS>
 __device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double2* X, const double2* Y) {
-  const int nt = d / TS, ntiles = nt * nt;
+  constexpr int TR = PB_TILE_ROWS(TS);
+  const int ntr = d / TR, ntc = d / TS, ntiles = ntr * ntc;
   for (int tile = tid; tile < ntiles; tile += PB_THREADS) {
-    const int ti = tile / nt, r0 = ti * TS, c0 = (tile - ti * nt) * TS;
-    double2 acc[TS][TS];
+    const int ti = tile / ntc, r0 = ti * TR, c0 = (tile - ti * ntc) * TS;
+    double2 acc[TR][TS];
 #pragma unroll
-    for (int i = 0; i < TS; i++)
+    for (int i = 0; i < TR; i++)
 #pragma unroll
       for (int j = 0; j < TS; j++) acc[i][j] = make_double2(0.0, 0.0);
     for (int k = 0; k < d; k++) {
-      double2 x[TS], y[TS];
+      double2 x[TR], y[TS];
 #pragma unroll
-      for (int i = 0; i < TS; i++) x[i] = X[(r0 + i) * d + k];
+      for (int i = 0; i < TR; i++) x[i] = X[(r0 + i) * d + k];
 #pragma unroll
       for (int j = 0; j < TS; j++) y[j] = Y[k * d + c0 + j];
 #pragma unroll
-      for (int i = 0; i < TS; i++)
+      for (int i = 0; i < TR; i++)
 #pragma unroll
         for (int j = 0; j < TS; j++) acc[i][j] = cfma(x[i], y[j], acc[i][j]);
     }
 #pragma unroll
-    for (int i = 0; i < TS; i++)
+    for (int i = 0; i < TR; i++)
 #pragma unroll
       for (int j = 0; j < TS; j++) C[(r0 + i) * d + c0 + j] = acc[i][j];
   }
@@ -41,17 +45,21 @@ __device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double
 }
 
 // Solve Q X = Pm in place (X overwrites Pm); Q is destroyed.  Gauss-Jordan with partial pivoting; d <= 32, so the
-// pivot search is one pass of warp 0 and the chosen row travels through s_piv.
+// pivot search is one pass of warp 0 and the chosen row travels through s_piv.  Pivot rows are NOT normalised inside
+// the loop (the factor carries 1/pivot; every row is divided by its own pivot once at the end): two block barriers
+// per pivot instead of four.  thread = (row, column group) in the elimination: the factor is computed once per thread.
 __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, int* s_piv) {
+  constexpr int CG = PB_THREADS / 32;
+  const int r = tid / CG, jg = tid - r * CG;
   for (int k = 0; k < d; k++) {
     if (tid < 32) {
       double best = -1.0;
       int brow = k;
-      const int r = k + tid;
-      if (r < d) {
-        const double2 v = Q[r * d + k];
+      const int rr = k + tid;
+      if (rr < d) {
+        const double2 v = Q[rr * d + k];
         best = v.x * v.x + v.y * v.y;
-        brow = r;
+        brow = rr;
       }
       for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -65,7 +73,7 @@ __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, 
     }
     __syncthreads();
     const int brow = *s_piv;
-    if (brow != k) {
+    if (brow != k) {  // block-uniform
       for (int j = tid; j < 2 * d; j += PB_THREADS) {
         double2* M = (j < d) ? Q : Pm;
         const int c = (j < d) ? j : j - d;
@@ -75,30 +83,30 @@ __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, 
       }
       __syncthreads();
     }
-    const double2 piv = Q[k * d + k];
-    const double inv_n = 1.0 / (piv.x * piv.x + piv.y * piv.y);
-    const double2 pinv = make_double2(piv.x * inv_n, -piv.y * inv_n);
-    __syncthreads();  // every thread has read the pivot before the row is scaled
-    for (int j = tid; j < 2 * d; j += PB_THREADS) {
-      double2* M = (j < d) ? Q : Pm;
-      const int c = (j < d) ? j : j - d;
-      if (j >= d || c >= k) M[k * d + c] = cmul(M[k * d + c], pinv);
-    }
-    __syncthreads();
-    // eliminate column k from every other row; columns <= k of Q are dead (never written: the factors stay readable)
-    const int w = 2 * d - (k + 1);  // live columns per row: Q columns k+1.., all of P
-    for (int e = tid; e < d * w; e += PB_THREADS) {
-      const int r = e / w, j = e - r * w + (k + 1);
-      if (r == k) continue;
-      double2* M = (j < d) ? Q : Pm;
-      const int c = (j < d) ? j : j - d;
-      const double2 f = Q[r * d + k];
-      const double2 p = M[k * d + c];
-      const double2 v = M[r * d + c];
-      M[r * d + c] = make_double2(v.x - (f.x * p.x - f.y * p.y), v.y - (f.x * p.y + f.y * p.x));
+    // eliminate column k from every other row.  Columns <= k of Q are dead (never written), so the pivot and the
+    // factors stay readable while the live columns are updated; row k itself is not touched.
+    if (r < d && r != k) {
+      const double2 piv = Q[k * d + k];
+      const double inv_n = 1.0 / (piv.x * piv.x + piv.y * piv.y);
+      const double2 f = cmul(Q[r * d + k], make_double2(piv.x * inv_n, -piv.y * inv_n));
+      for (int j = k + 1 + jg; j < 2 * d; j += CG) {
+        double2* M = (j < d) ? Q : Pm;
+        const int c = (j < d) ? j : j - d;
+        const double2 p = M[k * d + c];
+        const double2 v = M[r * d + c];
+        M[r * d + c] = make_double2(fma(-f.x, p.x, fma(f.y, p.y, v.x)), fma(-f.x, p.y, fma(-f.y, p.x, v.y)));
+      }
     }
     __syncthreads();
   }
+  // X[r][:] = P[r][:] / Q[r][r]
+  if (r < d) {
+    const double2 piv = Q[r * d + r];
+    const double inv_n = 1.0 / (piv.x * piv.x + piv.y * piv.y);
+    const double2 pinv = make_double2(piv.x * inv_n, -piv.y * inv_n);
+    for (int c = jg; c < d; c += CG) Pm[r * d + c] = cmul(Pm[r * d + c], pinv);
+  }
+  __syncthreads();
 }
 
 // expm(A) with four work matrices; returns the buffer holding the result (X1 or X2).  See wexpm (propagator.cu).
