@@ -1,6 +1,6 @@
 // casq_b200: piecewise-constant propagators U = prod_n expm(h G_F(t_n + h/2)) for batches of pulse points,
 // one warp per trajectory, all matrices in shared memory, for dim <= 16; a block per trajectory (propagator_block.cuh)
-// for 16 < dim <= 32.
+// for 16 < dim <= 64.
 //
 // This is the exponential-midpoint scheme of qiskit-dynamics' fixed-step "scipy_expm"/"jax_expm" solvers
 // (SURVEY.md Appendix A.5 last bullet).  casq's ODESolverMethod enum cannot select them
@@ -19,7 +19,7 @@
 
 #define PROP_MAXK 4
 #define PROP_WARPS 4   // warps (= trajectories) per block of the warp-per-trajectory kernel
-#define PROP_MAXD 32
+#define PROP_MAXD 64
 
 struct PropArgs {
   const double* table;  // [NT][W]: carriers then p_i at every stage time (midpoints are the odd entries)
@@ -39,6 +39,7 @@ struct PropArgs {
   const double2* U;  // frame basis
   const double2* env_tab;  // [KA][n_total][B] envelope samples (casq_env_table_kernel)
   int n_total;
+  double2* scratch;  // block kernel, dim > 32: [B][6][dim*dim] work matrices in global memory (NULL: shared memory)
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -425,7 +426,7 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
   }
   const int d = m->d;
   if (d < 2 || d > PROP_MAXD || KA > PROP_MAXK)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_propagators_expm: dim %d with %d active channels is outside the built kernel (dim <= 32)", d, KA);
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_propagators_expm: dim %d with %d active channels is outside the built kernels (dim <= 64)", d, KA);
   cudaStream_t st = (cudaStream_t)stream;
   CASQ_CUDA(cudaSetDevice(m->device));
   TimeGrid g;
@@ -505,8 +506,14 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
     CASQ_CUDA(casq_launch_env_table<PROP_MAXK>(KA, ds, params_dev, B, b0, Bc, n_total, (double2*)m->work2.p, st));
     a.B = Bc;
     a.out = out_dev + b0 * 2LL * n2;
-    if (d > 16) {  // a block per trajectory (propagator_block.cuh)
-      const size_t smem_b = (size_t)PROP_NBUF * n2 * sizeof(double2);
+    if (d > 16) {  // a block per trajectory (propagator_block.cuh); work matrices in shared memory up to dim 32
+      size_t smem_b = (size_t)PROP_NBUF * n2 * sizeof(double2);
+      a.scratch = nullptr;
+      if (d > 32) {
+        if ((rc = m->work3.ensure((size_t)Bc * smem_b))) return rc;
+        a.scratch = (double2*)m->work3.p;
+        smem_b = 0;
+      }
 #define PROP_BLOCK_LAUNCH(TS_)                                                                                                    \
   {                                                                                                                               \
     CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_block_kernel<TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); \

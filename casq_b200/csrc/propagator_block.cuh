@@ -1,4 +1,4 @@
-// casq_b200: propagators for 16 < dim <= 32 (three coupled transmons: dim 27), ONE BLOCK of 256 threads per trajectory.
+// casq_b200: propagators for 16 < dim <= 64 (three coupled transmons: dim 27), ONE BLOCK of 256 threads per trajectory.
 //
 // Six dim x dim work matrices are 70 kB at dim 27: with a warp per trajectory only two warps fit an SM and every
 // lane walks 23 matrix elements per product (the generic kernel: 1.0e3 unitaries/s at dim 27).  Here the 256 threads
@@ -6,6 +6,9 @@
 // 3 | dim, else 2 or 1: per k it loads 2 TS operands for TS^2 complex FMAs), the Gauss-Jordan elimination and all
 // element-wise passes are strided over the block, and three blocks (24 warps) are resident per SM.
 // Same algorithm as propagator.cu (orders 3/5/7/9 by Higham's theta_m, scaling above theta_9, partial pivoting).
+// Up to dim 32 the six work matrices live in shared memory; for 32 < dim <= 64 (393 kB at dim 64) they live in a
+// per-trajectory global scratch that stays L2 resident, reached through the same pointers (__syncthreads orders the
+// block's global writes and reads).
 #pragma once
 
 #define PB_THREADS 256
@@ -44,22 +47,24 @@ __device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double
   __syncthreads();
 }
 
-// Solve Q X = Pm in place (X overwrites Pm); Q is destroyed.  Gauss-Jordan with partial pivoting; d <= 32, so the
-// pivot search is one pass of warp 0 and the chosen row travels through s_piv.  Pivot rows are NOT normalised inside
+// Solve Q X = Pm in place (X overwrites Pm); Q is destroyed.  Gauss-Jordan with partial pivoting; the pivot search is
+// done by warp 0 (d <= 64: at most two rows per lane) and the chosen row travels through s_piv.  Pivot rows are NOT normalised inside
 // the loop (the factor carries 1/pivot; every row is divided by its own pivot once at the end): two block barriers
 // per pivot instead of four.  thread = (row, column group) in the elimination: the factor is computed once per thread.
 __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, int* s_piv) {
-  constexpr int CG = PB_THREADS / 32;
+  const int CG = PB_THREADS / (d > 32 ? 64 : 32);
   const int r = tid / CG, jg = tid - r * CG;
   for (int k = 0; k < d; k++) {
     if (tid < 32) {
       double best = -1.0;
       int brow = k;
-      const int rr = k + tid;
-      if (rr < d) {
+      for (int rr = k + tid; rr < d; rr += 32) {
         const double2 v = Q[rr * d + k];
-        best = v.x * v.x + v.y * v.y;
-        brow = rr;
+        const double mag = v.x * v.x + v.y * v.y;
+        if (mag > best) {
+          best = mag;
+          brow = rr;
+        }
       }
       for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -115,10 +120,13 @@ __device__ double2* bexpm(int d, int tid, double2* A, double2* X1, double2* X2, 
   const int n2 = d * d;
   for (int e = tid; e < n2; e += PB_THREADS) X4[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
   __syncthreads();
-  if (tid < 32) {  // ||A||_1: lane j sums column j (d <= 32), warp max
+  if (tid < 32) {  // ||A||_1: lane j sums columns j, j + 32 (d <= 64), warp max
     double s = 0.0;
-    if (tid < d)
-      for (int i = 0; i < d; i++) s += X4[i * d + tid].x;
+    for (int j = tid; j < d; j += 32) {
+      double cs = 0.0;
+      for (int i = 0; i < d; i++) cs += X4[i * d + j].x;
+      s = fmax(s, cs);
+    }
     for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
     if (tid == 0) *s_red = s;
   }
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(PB_THREADS) propagator_expm_block_kernel(const
   __shared__ double s_red;
   __shared__ int s_piv;
   const long long b = blockIdx.x;
-  double2* ws = reinterpret_cast<double2*>(smem_raw);
+  double2* ws = a.scratch ? a.scratch + (size_t)b * PROP_NBUF * n2 : reinterpret_cast<double2*>(smem_raw);
   double2 *A = ws, *Uacc = ws + n2, *X1 = ws + 2 * n2, *X2 = ws + 3 * n2, *X3 = ws + 4 * n2, *X4 = ws + 5 * n2;
   for (int e = tid; e < n2; e += PB_THREADS) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
   __syncthreads();

@@ -128,7 +128,7 @@ int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse_slot* slot
  * h <= max_dt (same step-count rule as RK4): the exponential-midpoint scheme of qiskit-dynamics'
  * "scipy_expm"/"jax_expm" solvers.  NOT selectable through casq's ODESolverMethod enum
  * (src/casq/backends/pulse_backend.py:60-71) -- additive API for full-unitary sweeps (BASELINE cfg 3).
- * expm = scaling-and-squaring Pade (Higham 2005; orders 3/5/7/9, scaled to theta_9 above it).  dim <= 32.
+ * expm = scaling-and-squaring Pade (Higham 2005; orders 3/5/7/9, scaled to theta_9 above it).  dim <= 64.
  *   out_dev [B*dim*dim] c128: propagators in the rotating frame, lab basis (apply to the state at t0). */
 int casq_propagators_expm(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
                           const double* params_dev, double t0, double t1, double max_dt, double* out_dev,

@@ -107,3 +107,27 @@ def test_propagators_match_oracle_d27_three_transmons():
                                       max_dt).cpu().numpy()
         assert got.shape == (B, 27, 27) and np.abs(got - want).max() < TOL_U, (rwa, max_dt)
         assert max(np.abs(u.conj().T @ u - np.eye(27)).max() for u in got) < 1e-11
+
+
+@pytest.mark.parametrize("d", [20, 40, 64])
+def test_propagators_match_oracle_random_hermitian_models_up_to_dim_64(d):
+    """16 < dim <= 64: the block-per-trajectory kernel (tiles of 2 at even dims; work matrices in shared memory up to
+    dim 32, in L2-resident global scratch above).  Random Hermitian H0 / drive with GHz-scale spectrum, full frame."""
+    rng = np.random.default_rng(100 + d)
+    def herm(scale):
+        m = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+        return scale * (m + m.conj().T) / 2
+    h0 = np.diag(np.sort(rng.uniform(0, 2 * np.pi * 5e9, d))).astype(complex) + herm(2 * np.pi * 5e6)
+    x = herm(2 * np.pi * 40e6)
+    carriers = {"d0": 4.9e9}
+    om = O.OracleModel(h0, x[None], ["d0"], carriers, DT, rotating_frame=h0)
+    nm = NativeModel(h0, x[None], [carriers["d0"]], DT, rotating_frame=h0)
+    B, dur = 2, 4
+    p = dict(amp=rng.uniform(0.3, 0.9, B), angle=rng.uniform(-1, 1, B), sigma=2.0)
+    samples = O.channel_samples(["d0"], [O.PulseSpec("gaussian", "d0", dur)], [p])
+    for max_dt in (DT / 4, 2 * DT):
+        want = O.expm_midpoint_propagators(om, samples, (0.0, dur * DT), max_dt)
+        got = engine.propagators_expm(nm, [("gaussian", 0, 0, dur)], engine.pack_params([p], device="cuda"), (0.0, dur * DT),
+                                      max_dt).cpu().numpy()
+        assert got.shape == (B, d, d) and np.abs(got - want).max() < TOL_U, (d, max_dt)
+        assert max(np.abs(u.conj().T @ u - np.eye(d)).max() for u in got) < 1e-10
