@@ -89,7 +89,7 @@ def test_propagators_match_oracle_d9_all_pade_orders(rwa):
 
 def test_propagators_match_oracle_d27_three_transmons():
     """dim 27 (three coupled transmons): the generic warp-per-trajectory kernel with two warps per block; unitaries of a
-    DRAG pulse on d1 against scipy's expm per step, with and without RWA, and an unsupported-size error above dim 32."""
+    DRAG pulse on d1 against scipy's expm per step, with and without RWA."""
     rng = np.random.default_rng(21)
     v = O.MANILA["vars"]
     qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(3)}
