@@ -88,7 +88,7 @@ def test_propagators_match_oracle_d9_all_pade_orders(rwa):
 
 
 def test_propagators_match_oracle_d27_three_transmons():
-    """dim 27 (three coupled transmons): the generic warp-per-trajectory kernel with two warps per block; unitaries of a
+    """dim 27 (three coupled transmons): the block-per-trajectory kernel with 3x3 register tiles; unitaries of a
     DRAG pulse on d1 against scipy's expm per step, with and without RWA."""
     rng = np.random.default_rng(21)
     v = O.MANILA["vars"]
