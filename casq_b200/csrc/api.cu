@@ -97,7 +97,7 @@ extern "C" int casq_solve_sv_rk4(casq_model* m, int n_slots, const casq_pulse_sl
   if (casq_general_supported(m, n_active))
     return casq_general_rk4(m, n_active, active, ds, n_total, B, params_dev, y0_dev, y0_batched, t0, t1, max_dt, T, t_eval,
                             out_dev, (cudaStream_t)stream);
-  CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_rk4: dim %d with %d active channels is outside the built kernels (dim <= 64, <= 4 channels)", m->d, n_active);
+  CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_rk4: dim %d with %d active channels is outside the built kernels (dim <= 256, <= 4 channels)", m->d, n_active);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -279,7 +279,7 @@ __global__ void sv_general_table_kernel(const double* __restrict__ times, long l
 }
 
 bool casq_general_supported(const casq_model* m, int n_active) {
-  return m->d >= 2 && m->d <= 64 && n_active >= 1 && n_active <= GEN_MAXK;
+  return m->d >= 2 && m->d <= 256 && n_active >= 1 && n_active <= GEN_MAXK;
 }
 
 int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& slots, int n_total, long long B,
@@ -319,7 +319,8 @@ int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& s
       }
     }
   const int G = d <= 16 ? 16 : 32;
-  const int R = (d + G - 1) / G;
+  int R = (d + G - 1) / G;
+  if (R > 4) R = 8;  // instantiated row counts: 1, 2, 3, 4, 8 (dim <= 256: the full 5-transmon model is 243)
   const int groups = 128 / G;
   size_t smem = (((size_t)ne * sizeof(int) + 15) & ~(size_t)15) + ne * 16 * (1 + (size_t)KA * (m->rwa ? 2 : 1)) +
                 (size_t)groups * R * G * 16;
@@ -404,7 +405,7 @@ int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& s
       sv_rk4_general_kernel<G_, R_, false><<<grid, 128, smem, st>>>(a);                                                 \
     }                                                                                                                   \
   }
-  GEN_LAUNCH(16, 1) GEN_LAUNCH(32, 1) GEN_LAUNCH(32, 2)
+  GEN_LAUNCH(16, 1) GEN_LAUNCH(32, 1) GEN_LAUNCH(32, 2) GEN_LAUNCH(32, 3) GEN_LAUNCH(32, 4) GEN_LAUNCH(32, 8)
 #undef GEN_LAUNCH
   CASQ_CUDA(cudaGetLastError());
   return CASQ_OK;

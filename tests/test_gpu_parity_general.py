@@ -135,3 +135,30 @@ def test_backend_solve_two_qubit_model_all_methods():
         s2 = backend.solve(circuit, m, run_options={"rtol": 1e-10, "atol": 1e-10})
         assert np.abs(s2.states[-1].data - truth).max() < 1e-5
         assert set(s2.populations[-1]) <= {"0", "1"} and sum(s2.counts[-1].values()) == 1024
+
+
+@pytest.mark.parametrize("subsystems,dim,rwa", [([0, 1, 2, 3], 81, None), (None, 243, 3.0e9)])
+def test_four_and_five_transmons_rk4_in_the_diagonal_frame(subsystems, dim, rwa):
+    """dim 81 and the FULL ibmq_manila model (dim 243, what casq's from_backend builds, in its default diagonal frame):
+    3, 4 or 8 rows of the state per lane, sparse rows (exchange couplings + one drive) in shared memory."""
+    rng = np.random.default_rng(dim)
+    om, nm, ch = _pair(O.MANILA, subsystems, "diag", rwa)
+    assert om.dim == dim
+    B, dur = 3, 6
+    specs = [O.PulseSpec("drag", "d1", dur)]
+    ps = [dict(amp=rng.uniform(0.2, 0.8, B), angle=rng.uniform(-1, 1, B), sigma=2.0, beta=rng.uniform(-1, 1, B))]
+    samples = O.channel_samples(ch, specs, ps)
+    y0 = rng.normal(size=(B, dim)) + 1j * rng.normal(size=(B, dim))
+    y0 /= np.linalg.norm(y0, axis=1, keepdims=True)
+    span = (0.0, dur * DT)
+    sub = 8 if rwa else 40
+    _, want = O.rk4_solve(om, samples, y0, span, DT / sub)
+    got = engine.solve_sv_rk4(nm, [("drag", ch.index("d1"), 0, dur)], engine.pack_params(ps, device="cuda"), y0, span, DT / sub).cpu().numpy()
+    assert got.shape == (B, 2, dim) and np.abs(got - want).max() < TOL_STATE
+    # the dressed (full-matrix) frame makes the operators dense: a clean "unsupported", not a wrong answer
+    if dim == 243:
+        st, ops, chs, _ = O.parse_hamiltonian_dict(O.MANILA, None)
+        dense = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in chs], DT, rotating_frame=st)
+        from casq_b200.common.exceptions import CasqError
+        with pytest.raises(CasqError, match="too dense"):
+            engine.solve_sv_rk4(dense, [("drag", chs.index("d1"), 0, dur)], engine.pack_params(ps, device="cuda"), y0, span, DT / 8)
