@@ -422,7 +422,7 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
   const int d = m->d;
   const bool small_path = d >= 2 && d <= DP_MAXD && KA <= DP_MAXK;
   if (!small_path && !casq_dopri5_general_supported(m, KA))
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: dim %d with %d active channels is outside the built kernels (dim <= 64, <= 4 channels)", d, KA);
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: dim %d with %d active channels is outside the built kernels (dim <= 256, <= 4 channels)", d, KA);
   cudaStream_t st = (cudaStream_t)stream;
   CASQ_CUDA(cudaSetDevice(m->device));
 

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(32 * DG_WARPS) sv_dopri5_general_kernel(const 
 }
 
 bool casq_dopri5_general_supported(const casq_model* m, int n_active) {
-  return m->d >= 2 && m->d <= 64 && n_active >= 1 && n_active <= DG_MAXK;
+  return m->d >= 2 && m->d <= 256 && n_active >= 1 && n_active <= DG_MAXK;
 }
 
 int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots& slots, int n_total, long long B,
@@ -426,11 +426,13 @@ int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots
         h_col[e] = i;
       }
     }
-  const int R = d <= 32 ? 1 : 2;
+  // rows of the state per lane: 1, 2, 4 or 8.  From 4 up the seven stage vectors no longer fit the register file and
+  // live in (L1-cached) local memory: the large models (4 and 5 transmons) run, at a lower rate per flop.
+  const int R = d <= 32 ? 1 : (d <= 64 ? 2 : (d <= 128 ? 4 : 8));
   const size_t smem = (((size_t)ne * sizeof(int) + 15) & ~(size_t)15) + ne * 16 * (1 + (size_t)KA * (m->rwa ? 2 : 1)) +
                       (size_t)DG_WARPS * R * 32 * 16;
   if (smem > 200 * 1024)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "general Dopri5: operators too dense for shared memory (dim %d, row width %d, %d channels)", d, width, KA);
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "general Dopri5: operators too dense for shared memory (dim %d, row width %d, %d channels): large models need a diagonal rotating frame (rotating_frame = diag(static_operator), casq's from_backend default)", d, width, KA);
   const int TM = (int)pts.size();
   const size_t ell_bytes = ne * sizeof(int) + 16 + ne * 16 * (1 + 2 * (size_t)KA);
   int rc;
@@ -507,8 +509,12 @@ int casq_dopri5_general(casq_model* m, int KA, const int* active, const DevSlots
     const unsigned grid = (unsigned)((Bc + DG_WARPS - 1) / DG_WARPS);
     if (R == 1 && m->rwa) DG_LAUNCH(1, true)
     else if (R == 1) DG_LAUNCH(1, false)
-    else if (m->rwa) DG_LAUNCH(2, true)
-    else DG_LAUNCH(2, false)
+    else if (R == 2 && m->rwa) DG_LAUNCH(2, true)
+    else if (R == 2) DG_LAUNCH(2, false)
+    else if (R == 4 && m->rwa) DG_LAUNCH(4, true)
+    else if (R == 4) DG_LAUNCH(4, false)
+    else if (m->rwa) DG_LAUNCH(8, true)
+    else DG_LAUNCH(8, false)
   }
 #undef DG_LAUNCH
   CASQ_CUDA(cudaGetLastError());

@@ -325,7 +325,7 @@ int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& s
   size_t smem = (((size_t)ne * sizeof(int) + 15) & ~(size_t)15) + ne * 16 * (1 + (size_t)KA * (m->rwa ? 2 : 1)) +
                 (size_t)groups * R * G * 16;
   if (smem > 200 * 1024)
-    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "general RK4: operators too dense for shared memory (dim %d, row width %d, %d channels)", d, width, KA);
+    CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "general RK4: operators too dense for shared memory (dim %d, row width %d, %d channels): large models need a diagonal rotating frame (rotating_frame = diag(static_operator), casq's from_backend default)", d, width, KA);
 
   // ---- time grid + table
   TimeGrid g;

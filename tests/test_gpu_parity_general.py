@@ -162,3 +162,22 @@ def test_four_and_five_transmons_rk4_in_the_diagonal_frame(subsystems, dim, rwa)
         from casq_b200.common.exceptions import CasqError
         with pytest.raises(CasqError, match="too dense"):
             engine.solve_sv_rk4(dense, [("drag", chs.index("d1"), 0, dur)], engine.pack_params(ps, device="cuda"), y0, span, DT / 8)
+
+
+@pytest.mark.parametrize("subsystems,dim", [([0, 1, 2, 3], 81), (None, 243)])
+def test_four_and_five_transmons_dopri5_in_the_diagonal_frame(subsystems, dim):
+    """Adaptive Dopri5 on the large models (4 / 8 state rows per lane, stage vectors in local memory): constant envelope
+    over a window longer than the span, so the controller must follow the oracle's accept / reject sequence exactly."""
+    rng = np.random.default_rng(7 * dim)
+    om, nm, ch = _pair(O.MANILA, subsystems, "diag", 3.0e9)
+    B = 2
+    p = dict(amp=rng.uniform(0.3, 0.8, B), angle=rng.uniform(-1, 1, B))
+    samples = O.channel_samples(ch, [O.PulseSpec("constant", "d1", 8)], [p])
+    y0 = rng.normal(size=(B, dim)) + 1j * rng.normal(size=(B, dim))
+    y0 /= np.linalg.norm(y0, axis=1, keepdims=True)
+    span = (0.0, 3 * DT)
+    _, want, steps = O.dopri5_jax_solve(om, samples, y0, span, rtol=1e-8, atol=1e-8)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("constant", ch.index("d1"), 0, 8)], engine.pack_params([p], device="cuda"), y0, span,
+                                             rtol=1e-8, atol=1e-8, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-11
