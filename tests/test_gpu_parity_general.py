@@ -181,3 +181,32 @@ def test_four_and_five_transmons_dopri5_in_the_diagonal_frame(subsystems, dim):
                                              rtol=1e-8, atol=1e-8, return_stats=True)
     assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)
     assert np.abs(got.cpu().numpy() - want).max() < 1e-11
+
+
+def test_backend_solve_full_five_qubit_model_matches_oracle_flow():
+    """The drop-in call on the model casq builds from a backend: all five ibmq_manila transmons (dim 243) in the diagonal
+    frame, a DRAG gate on qubit 0, fixed-step RK4 and the default adaptive method; states, populations and
+    counts against the oracle's restatement of casq's flow."""
+    from casq_b200.backends import BackendLibrary, PulseBackend, build
+    from casq_b200.gates import DragPulseGate, PulseCircuit
+    from casq_b200.models import ControlModel, TransmonModel
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, None)
+    h = TransmonModel.manila(rotating_frame=np.diag(st).real, rwa_cutoff_freq=3.0e9)
+    c = ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+    backend = build(BackendLibrary.B200, h, c, seed=7)
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=np.diag(st).real, rwa_cutoff_freq=3.0e9)
+    gate = DragPulseGate(duration=8, amplitude=0.8)
+    circuit = PulseCircuit.from_pulse_gate(gate, {"sigma": 2.0, "beta": 0.5})
+    spec, par = [O.PulseSpec("drag", "d0", 8)], [dict(amp=0.8, angle=0.0, sigma=2.0, beta=0.5)]
+    M = PulseBackend.ODESolverMethod
+    sol = backend.solve(circuit, M.QISKIT_DYNAMICS_RK4, steps=3, run_options={"max_dt": DT / 8})
+    ref = O.casq_solve(om, spec, par, method="RK4", steps=3, run_options={"max_dt": DT / 8})
+    got = np.array([s.data for s in sol.states])
+    assert got.shape == (3, 243) and np.abs(got - ref["states"][0]).max() < TOL_STATE
+    for a, b in zip(sol.populations, ref["populations"]):
+        assert all(set(k) <= {"0", "1"} for k in a)  # bit-string keys of the measured memory slots, levels > 1 folded
+        assert all(abs(a.get(k, 0.0) - b.get(k, 0.0)) < 1e-9 for k in set(a) | set(b))
+    assert abs(sum(sol.populations[-1].values()) - 1.0) < 1e-9 and sum(sol.counts[-1].values()) == 1024
+    s2 = backend.solve(circuit, M.QISKIT_DYNAMICS_JAX_ODEINT)
+    truth = O.casq_solve(om, spec, par, method="DOP853", run_options={"rtol": 1e-11, "atol": 1e-11})["states"][0, -1]
+    assert np.abs(s2.states[-1].data - truth).max() < 1e-4
