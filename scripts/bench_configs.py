@@ -105,6 +105,19 @@ def main():
             best, _ = timed(rung, reps=2, warm=1)
             res[f"extra_dopri5_general_d{dg}"] = {"B": Bg, "ms_best": best, "traj_per_s": Bg / best * 1e3,
                                                   "attempted_steps_total": int(outg["r"][1][:, 0].sum()), "failed": int((outg["r"][2] != 0).sum())}
+        # three-transmon unitaries (block-per-trajectory propagator kernel) and the full five-transmon state-vector solve
+        st3, ops3, ch3 = P.chain(3)
+        nm3 = P.native(st3, ops3, ch3, rwa=0.75 * P.CARRIERS["d0"])
+        B27 = 1024
+        p27 = engine.pack_params([dict(amp=rng.uniform(0.05, 0.8, B27), angle=0.0, sigma=64.0, width=rng.uniform(0, 768, B27))], device="cuda")
+        best, _ = timed(lambda: engine.propagators_expm(nm3, [("gaussian_square", ch3.index("u0"), 0, 1024)], p27, (0, 1024 * DT), DT), reps=2, warm=1)
+        res["extra_expm_block_d27"] = {"B": B27, "steps": 1024, "ms_best": best, "traj_per_s": B27 / best * 1e3}
+        nm5s = P.native(st5m, ops5, ch5, frame="diag", rwa=0.75 * P.CARRIERS["d0"])
+        B243 = 4096
+        p243 = engine.pack_params([dict(amp=np.linspace(0.05, 0.5, B243), angle=0.0, sigma=64.0, beta=1.0)], device="cuda")
+        y243 = np.zeros(243, dtype=complex); y243[0] = 1
+        best, _ = timed(lambda: engine.solve_sv_rk4(nm5s, [("drag", ch5.index("d0"), 0, 256)], p243, y243, (0, 257 * DT), DT / 4), reps=2, warm=1)
+        res["extra_rk4_general_d243"] = {"B": B243, "steps": 1028, "ms_best": best, "traj_per_s": B243 / best * 1e3}
     txt = json.dumps(res, indent=1)
     print(txt)
     if args.out:
