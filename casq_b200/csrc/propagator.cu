@@ -47,6 +47,56 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
   return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
 
+// z_k = envelope sample (per-solve table) x carrier phase at the midpoint entry `pm` of the stage table, for every driven
+// channel; shared by the warp-per-trajectory and the block-per-trajectory kernels.
+__device__ __forceinline__ void prop_signals(const PropArgs& a, long long b, long long pm, double* zr, double* zi) {
+  const int gidx = __ldg(a.idx + pm);
+  const bool inside = gidx >= 0 && gidx < a.n_total;
+  const double* ent = a.table + pm * a.W;
+#pragma unroll
+  for (int k = 0; k < PROP_MAXK; k++) {
+    zr[k] = zi[k] = 0.0;
+    if (k < a.KA && inside) {
+      const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
+      const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
+      zr[k] = env.x * c - env.y * sn;
+      zi[k] = env.x * sn + env.y * c;
+    }
+  }
+}
+
+// A = h * (-i) * p_i conj(p_j) (S + sum_k z_k P_k + conj(z_k) N_k), elements strided over NT cooperating threads.  The
+// operators are read through L1 (the same few kB for every trajectory of the grid): shared memory is kept for the work
+// matrices.
+template <int DT>
+__device__ __forceinline__ void prop_assemble(const PropArgs& a, int d_, long long pm, const double* zr, const double* zi, double h,
+                                              double2* A, int tid, int nthreads) {
+  const int d = DT > 0 ? DT : d_, n2 = d * d;
+  const double2* ph = reinterpret_cast<const double2*>(a.table + pm * a.W + 2 * a.KA);
+  for (int e = tid; e < n2; e += nthreads) {
+    const int i = e / d, j = e - i * d;
+    double2 m = __ldg(a.S + e);
+#pragma unroll
+    for (int k = 0; k < PROP_MAXK; k++) {
+      if (k < a.KA) {
+        const double2 P = __ldg(a.P + (size_t)k * n2 + e);
+        if (a.rwa) {
+          const double2 N = __ldg(a.N + (size_t)k * n2 + e);
+          m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
+          m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
+        } else {
+          m.x = fma(zr[k], P.x, m.x);
+          m.y = fma(zr[k], P.y, m.y);
+        }
+      }
+    }
+    const double2 pi_ = __ldg(ph + i), pj = __ldg(ph + j);
+    const double2 f = make_double2(pi_.x * pj.x + pi_.y * pj.y, pi_.y * pj.x - pi_.x * pj.y);  // p_i conj(p_j)
+    const double2 g = cmul(f, m);
+    A[e] = make_double2(h * g.y, -h * g.x);  // -i g
+  }
+}
+
 // C = X * Y (d x d), warp-cooperative; C must not alias X or Y.
 template <int DT>
 __device__ __forceinline__ void wmatmul(int d_, int lane, double2* C, const double2* X, const double2* Y) {
@@ -308,7 +358,7 @@ __device__ double2* wexpm(int d_, int lane, double2* A, double2* X1, double2* X2
 
 template <int DT>
 __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_expm_kernel(const PropArgs a) {
-  const int d = DT > 0 ? DT : a.d, KA = a.KA, n2 = d * d;
+  const int d = DT > 0 ? DT : a.d, n2 = d * d;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -324,47 +374,9 @@ __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_e
     const double h = a.piece_h[p];
     for (int s = 0; s < n; s++) {
       const long long pm = pos + 1;  // midpoint entry
-      // envelope samples come from the per-solve table: with one step per sample (m = 1) the on-the-fly evaluation
-      // (2 exp, sincos, divisions) ran on every step
-      const int gidx = __ldg(a.idx + pm);
-      const bool inside = gidx >= 0 && gidx < a.n_total;
-      const double* ent = a.table + pm * a.W;
       double zr[PROP_MAXK], zi[PROP_MAXK];
-#pragma unroll
-      for (int k = 0; k < PROP_MAXK; k++) {
-        zr[k] = zi[k] = 0.0;
-        if (k < KA && inside) {
-          const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
-          const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
-          zr[k] = env.x * c - env.y * sn;
-          zi[k] = env.x * sn + env.y * c;
-        }
-      }
-      const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
-      // A = h * (-i) * p_i conj(p_j) (S + sum_k z_k P_k + conj(z_k) N_k); the operators are read through L1 (they are
-      // the same 4 kB for every warp of the grid), shared memory is kept for the per-warp work matrices
-      for (int e = lane; e < n2; e += 32) {
-        const int i = e / d, j = e - i * d;
-        double2 m = __ldg(a.S + e);
-#pragma unroll
-        for (int k = 0; k < PROP_MAXK; k++) {
-          if (k < KA) {
-            const double2 P = __ldg(a.P + (size_t)k * n2 + e);
-            if (a.rwa) {
-              const double2 N = __ldg(a.N + (size_t)k * n2 + e);
-              m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
-              m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
-            } else {
-              m.x = fma(zr[k], P.x, m.x);
-              m.y = fma(zr[k], P.y, m.y);
-            }
-          }
-        }
-        const double2 pi_ = __ldg(ph + i), pj = __ldg(ph + j);
-        const double2 f = make_double2(pi_.x * pj.x + pi_.y * pj.y, pi_.y * pj.x - pi_.x * pj.y);  // p_i conj(p_j)
-        const double2 g = cmul(f, m);
-        A[e] = make_double2(h * g.y, -h * g.x);  // -i g
-      }
+      prop_signals(a, b, pm, zr, zi);
+      prop_assemble<DT>(a, d, pm, zr, zi, h, A, lane, 32);
       __syncwarp();
       double2* E = wexpm<DT>(d, lane, A, X1, X2, X3, X4);
       wmatmul<DT>(d, lane, X4, E, Uacc);  // X4 is free once the odd polynomial has been consumed
@@ -514,10 +526,14 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
         a.scratch = (double2*)m->work3.p;
         smem_b = 0;
       }
-#define PROP_BLOCK_LAUNCH(TS_)                                                                                                    \
-  {                                                                                                                               \
-    CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_block_kernel<TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); \
-    propagator_expm_block_kernel<TS_><<<(unsigned)Bc, PB_THREADS, smem_b, st>>>(a);                                               \
+#define PROP_BLOCK_LAUNCH(TS_)                                                                                                             \
+  {                                                                                                                                        \
+    if (a.scratch) {                                                                                                                       \
+      propagator_expm_block_kernel<TS_, true><<<(unsigned)Bc, PB_THREADS, 0, st>>>(a);                                                     \
+    } else {                                                                                                                               \
+      CASQ_CUDA(cudaFuncSetAttribute(propagator_expm_block_kernel<TS_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b)); \
+      propagator_expm_block_kernel<TS_, false><<<(unsigned)Bc, PB_THREADS, smem_b, st>>>(a);                                               \
+    }                                                                                                                                      \
   }
       if (d % 3 == 0) PROP_BLOCK_LAUNCH(3)
       else if (d % 2 == 0) PROP_BLOCK_LAUNCH(2)

@@ -51,8 +51,9 @@ __device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double
 // done by warp 0 (d <= 64: at most two rows per lane) and the chosen row travels through s_piv.  Pivot rows are NOT normalised inside
 // the loop (the factor carries 1/pivot; every row is divided by its own pivot once at the end): two block barriers
 // per pivot instead of four.  thread = (row, column group) in the elimination: the factor is computed once per thread.
+template <int ROWS>  // 32 or 64: padded row count (d <= ROWS)
 __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, int* s_piv) {
-  const int CG = PB_THREADS / (d > 32 ? 64 : 32);
+  constexpr int CG = PB_THREADS / ROWS;
   const int r = tid / CG, jg = tid - r * CG;
   for (int k = 0; k < d; k++) {
     if (tid < 32) {
@@ -115,7 +116,7 @@ __device__ __forceinline__ void bsolve(int d, int tid, double2* Q, double2* Pm, 
 }
 
 // expm(A) with four work matrices; returns the buffer holding the result (X1 or X2).  See wexpm (propagator.cu).
-template <int TS>
+template <int TS, int ROWS>
 __device__ double2* bexpm(int d, int tid, double2* A, double2* X1, double2* X2, double2* X3, double2* X4, double* s_red, int* s_piv) {
   const int n2 = d * d;
   for (int e = tid; e < n2; e += PB_THREADS) X4[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
@@ -196,7 +197,7 @@ __device__ double2* bexpm(int d, int tid, double2* A, double2* X1, double2* X2, 
     X1[e] = make_double2(v.x + u.x, v.y + u.y);
   }
   __syncthreads();
-  bsolve(d, tid, X3, X1, s_piv);
+  bsolve<ROWS>(d, tid, X3, X1, s_piv);
   double2 *E = X1, *Sq = X2;
   for (int q = 0; q < s; q++) {
     bmatmul<TS>(d, tid, Sq, E, E);
@@ -207,14 +208,16 @@ __device__ double2* bexpm(int d, int tid, double2* A, double2* X1, double2* X2, 
   return E;
 }
 
-template <int TS>
+// GWS: work matrices in the global scratch (dim > 32); a compile-time switch, so that in the shared-memory case the
+// compiler still knows every matrix pointer is shared (generic loads cost 15 % at dim 27).
+template <int TS, bool GWS>
 __global__ void __launch_bounds__(PB_THREADS) propagator_expm_block_kernel(const PropArgs a) {
-  const int d = a.d, KA = a.KA, n2 = d * d, tid = threadIdx.x;
+  const int d = a.d, n2 = d * d, tid = threadIdx.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red;
   __shared__ int s_piv;
   const long long b = blockIdx.x;
-  double2* ws = a.scratch ? a.scratch + (size_t)b * PROP_NBUF * n2 : reinterpret_cast<double2*>(smem_raw);
+  double2* ws = GWS ? a.scratch + (size_t)b * PROP_NBUF * n2 : reinterpret_cast<double2*>(smem_raw);
   double2 *A = ws, *Uacc = ws + n2, *X1 = ws + 2 * n2, *X2 = ws + 3 * n2, *X3 = ws + 4 * n2, *X4 = ws + 5 * n2;
   for (int e = tid; e < n2; e += PB_THREADS) Uacc[e] = make_double2((e / d) == (e % d) ? 1.0 : 0.0, 0.0);
   __syncthreads();
@@ -225,45 +228,11 @@ __global__ void __launch_bounds__(PB_THREADS) propagator_expm_block_kernel(const
     const double h = a.piece_h[p];
     for (int s = 0; s < n; s++) {
       const long long pm = pos + 1;  // midpoint entry
-      const int gidx = __ldg(a.idx + pm);
-      const bool inside = gidx >= 0 && gidx < a.n_total;
-      const double* ent = a.table + pm * a.W;
       double zr[PROP_MAXK], zi[PROP_MAXK];
-#pragma unroll
-      for (int k = 0; k < PROP_MAXK; k++) {
-        zr[k] = zi[k] = 0.0;
-        if (k < KA && inside) {
-          const double2 env = __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b);
-          const double c = __ldg(ent + 2 * k), sn = __ldg(ent + 2 * k + 1);
-          zr[k] = env.x * c - env.y * sn;
-          zi[k] = env.x * sn + env.y * c;
-        }
-      }
-      const double2* ph = reinterpret_cast<const double2*>(ent + 2 * KA);
-      for (int e = tid; e < n2; e += PB_THREADS) {
-        const int i = e / d, j = e - i * d;
-        double2 m = __ldg(a.S + e);
-#pragma unroll
-        for (int k = 0; k < PROP_MAXK; k++) {
-          if (k < KA) {
-            const double2 P = __ldg(a.P + (size_t)k * n2 + e);
-            if (a.rwa) {
-              const double2 N = __ldg(a.N + (size_t)k * n2 + e);
-              m.x += zr[k] * (P.x + N.x) - zi[k] * (P.y - N.y);
-              m.y += zr[k] * (P.y + N.y) + zi[k] * (P.x - N.x);
-            } else {
-              m.x = fma(zr[k], P.x, m.x);
-              m.y = fma(zr[k], P.y, m.y);
-            }
-          }
-        }
-        const double2 pi_ = __ldg(ph + i), pj = __ldg(ph + j);
-        const double2 f = make_double2(pi_.x * pj.x + pi_.y * pj.y, pi_.y * pj.x - pi_.x * pj.y);  // p_i conj(p_j)
-        const double2 g = cmul(f, m);
-        A[e] = make_double2(h * g.y, -h * g.x);  // -i g
-      }
+      prop_signals(a, b, pm, zr, zi);
+      prop_assemble<0>(a, d, pm, zr, zi, h, A, tid, PB_THREADS);
       __syncthreads();
-      double2* E = bexpm<TS>(d, tid, A, X1, X2, X3, X4, &s_red, &s_piv);
+      double2* E = bexpm<TS, (GWS ? 64 : 32)>(d, tid, A, X1, X2, X3, X4, &s_red, &s_piv);
       bmatmul<TS>(d, tid, X4, E, Uacc);  // X4 is free once the odd polynomial has been consumed
       double2* t = Uacc;
       Uacc = X4;
