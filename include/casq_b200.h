@@ -106,6 +106,9 @@ int casq_envelope_sample(int kind, int duration, int64_t B, const double* params
  *   y0_dev   [dim] (y0_batched=0) or [B*dim] c128, lab basis, state at t0 (frame transform is identity at t0=0)
  *   t_eval   host [T] or NULL (-> outputs at t0 and t1, T must be 2)
  *   out_dev  [B*T*dim] c128: states "in the rotating frame, lab basis" = what Solver.solve returns.
+ * Both solvers: dim <= 4 with <= 2 driven channels on the register kernels, otherwise dim <= 256 with <= 4 driven
+ * channels (sparse operator rows in shared memory: above dim ~64 that needs a diagonal rotating frame, casq's
+ * from_backend default; CASQ_ERR_UNSUPPORTED otherwise).
  * casq_solve_sv_rk4: ODESolverMethod.QISKIT_DYNAMICS_RK4 (pulse_backend.py:63): classical RK4, the span
  * cut at every t_eval point, each piece in n = ceil-ish(|D|/max_dt) equal steps (upstream rule). */
 int casq_solve_sv_rk4(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
