@@ -74,6 +74,9 @@ struct casq_model {
   DeviceBuf tab, tab_idx, tab_times, pieces_n, pieces_h, consts, work0, work1, work2, work3;
   // cache key of the table currently resident in `tab`
   std::string tab_key;
+  // second stream + fork/join events of the Lindblad path (several parts of the batch in flight fill each other's grid tails)
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 // hermitian eigen-decomposition (cyclic complex Jacobi); eigenvalues ascending, columns of V.

@@ -342,16 +342,10 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     CASQ_CUDA(cudaGetLastError());
   }
   unsigned char* dev = (unsigned char*)m->work1.p;
-  double2* bufs[4];  // y, y1, y2, y3
-  for (int i = 0; i < 4; i++) bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_pad;
-  {
-    const long long n = (long long)B * n_per;
-    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, ld, B, (const double2*)rho0_dev, rho0_batched, bufs[0]);
-    CASQ_CUDA(cudaGetLastError());
-  }
+  if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
   LbArgs a;
   memset(&a, 0, sizeof(a));
-  a.d = d; a.ld = ld; a.B = B;
+  a.d = d; a.ld = ld;
   a.KA = KA; a.NF = NF; a.NTF = NTF; a.NQ = NQ; a.NU = NU; a.NG = NG; a.NP = (int)grp_pairs.size() / 2; a.W = W;
   a.grp_start = (const int*)(dev + o_gstart);
   a.q_delta = (const int*)(dev + o_qdelta);
@@ -366,6 +360,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   a.table = (const double*)m->tab.p;
   a.idx = (const int*)m->tab_idx.p;
   a.params = params_dev;
+  a.Bp = B;
   a.slots = ds;
   a.cdense = cdense.empty() ? nullptr : (const double2*)(dev + o_cd);
   a.pair_ij = (const int*)(dev + o_pij);
@@ -373,23 +368,75 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "too many two-sided classes for the structured Lindblad kernel (%d classes, %d pairs)", NU, NP);
   const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
-  if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
-  const dim3 grid_pairs((unsigned)(pair_ij.size() / 2), (unsigned)B);
   const size_t smem_stage = lindblad_stage_smem(NQ, NU, NG);
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
 
+  // The batch runs as two (CASQ_LB_PARTS: up to four) parts on as many streams: every stage is its own grid and ends in a partly filled wave
+  // (4.3 waves at B = 128), and the blocks of the other parts fill that tail.  Each part has its own slice of every
+  // per-trajectory workspace; the tables are shared.
+  struct Part {
+    LbArgs a;
+    LbLists lists;
+    double2 *cq, *cu, *bufs[4];
+    long long b0, Bc;
+    cudaStream_t st;
+  };
+  int n_parts = (int)std::min<long long>(4, std::max<long long>(1, B / 16));  // measured at d = 243, B = 128: 161 / 178 / 183 / 184 traj/s for 1 / 2 / 3 / 4 parts
+  if (const char* e = getenv("CASQ_LB_PARTS")) n_parts = std::min(4, std::max(1, atoi(e)));  // tuning knob
+  n_parts = (int)std::min<long long>(n_parts, B);
+  if (n_parts > 1 && !m->ev_fork) CASQ_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i + 1 < n_parts; i++)
+    if (!m->aux_stream[i]) {
+      CASQ_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));
+      CASQ_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+    }
+  Part parts[4];
+  const size_t nu1 = (size_t)std::max(NU, 1), ng1 = (size_t)std::max(NG, 1);
+  for (int pi = 0; pi < n_parts; pi++) {
+    Part& P = parts[pi];
+    P.b0 = (long long)B * pi / n_parts;
+    P.Bc = (long long)B * (pi + 1) / n_parts - P.b0;
+    P.st = pi == 0 ? st : m->aux_stream[pi - 1];
+    P.a = a;
+    P.a.B = P.Bc;
+    P.a.b0 = P.b0;
+    for (int i = 0; i < 4; i++) P.bufs[i] = (double2*)m->work2.p + (size_t)i * B * n_pad + (size_t)P.b0 * n_pad;
+    P.cq = cq_all + 3 * (size_t)P.b0 * NQ * d;
+    P.cu = cu_all + 3 * (size_t)P.b0 * nu1 * d;
+    const size_t r0 = 3 * (size_t)P.b0 * d;  // first row of this part in every list array
+    P.lists.lcoef = lists.lcoef + r0 * NQ;
+    P.lists.loff = lists.loff + r0 * NQ;
+    P.lists.glist = lists.glist + r0 * ng1;
+    P.lists.lcnt = lists.lcnt + r0;
+    P.lists.gcnt = lists.gcnt + r0;
+  }
+  if (n_parts > 1) {  // fork: the other streams start after the table uploads and the table kernel
+    CASQ_CUDA(cudaEventRecord(m->ev_fork, st));
+    for (int i = 0; i + 1 < n_parts; i++) CASQ_CUDA(cudaStreamWaitEvent(m->aux_stream[i], m->ev_fork, 0));
+  }
+  for (int pi = 0; pi < n_parts; pi++) {
+    Part& P = parts[pi];
+    const long long n = P.Bc * (long long)n_per;
+    const double2* r0p = (const double2*)rho0_dev + (rho0_batched ? (size_t)P.b0 * n_per : 0);
+    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, r0p, rho0_batched, P.bufs[0]);
+    CASQ_CUDA(cudaGetLastError());
+  }
   int t_slot = 0;
   auto emit = [&]() -> int {
-    if (out_rho_dev) {
-      const long long n = (long long)B * n_per;
-      lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, ld, B, bufs[0], (double2*)out_rho_dev, T, t_slot);
-      CASQ_CUDA(cudaGetLastError());
-    }
-    if (out_pops_dev) {
-      lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)B), 256, 0, st>>>(d, ld, bufs[0], (const double2*)(dev + o_V),
-                                                                        (const double2*)(dev + o_ph) + (size_t)t_slot * d, out_pops_dev, T,
-                                                                        t_slot);
-      CASQ_CUDA(cudaGetLastError());
+    for (int pi = 0; pi < n_parts; pi++) {
+      Part& P = parts[pi];
+      if (out_rho_dev) {
+        const long long n = P.Bc * (long long)n_per;
+        lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, P.bufs[0],
+                                                                              (double2*)out_rho_dev + (size_t)P.b0 * T * n_per, T, t_slot);
+        CASQ_CUDA(cudaGetLastError());
+      }
+      if (out_pops_dev) {
+        lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)P.Bc), 256, 0, P.st>>>(d, ld, P.bufs[0], (const double2*)(dev + o_V),
+                                                                                (const double2*)(dev + o_ph) + (size_t)t_slot * d,
+                                                                                out_pops_dev + (size_t)P.b0 * T * d, T, t_slot);
+        CASQ_CUDA(cudaGetLastError());
+      }
     }
     t_slot++;
     return CASQ_OK;
@@ -400,26 +447,34 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     const int n = g.piece_nsteps[p];
     const double h_piece = g.piece_h[p];
     for (int s = 0; s < n; s++) {
-      // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
-      lindblad_coef_kernel<<<dim3((unsigned)B, 3), 256, smem_coef, st>>>(a, pos, cq_all, cu_all, lists);
-      // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
-      for (int stage = 1; stage <= 4; stage++) {
-        const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
-        LbStage sg;
-        sg.in = bufs[stage - 1];
-        sg.y = bufs[0];
-        sg.y1 = bufs[1];
-        sg.y2 = bufs[2];
-        sg.out = stage == 4 ? bufs[0] : bufs[stage];
-        sg.stage = stage;
-        sg.h = h_piece;
-        lindblad_stage_kernel<<<grid_pairs, 512, smem_stage, st>>>(a, lists, cu_all, set, sg);
+      // launches of the two parts are interleaved step by step so that neither stream's queue runs dry
+      for (int pi = 0; pi < n_parts; pi++) {
+        Part& P = parts[pi];
+        const dim3 grid_pairs((unsigned)(pair_ij.size() / 2), (unsigned)P.Bc);
+        lindblad_coef_kernel<<<dim3((unsigned)P.Bc, 3), 256, smem_coef, P.st>>>(P.a, pos, P.cq, P.cu, P.lists);
+        // stage 1: in = y (bufs[0]) -> y1 (bufs[1]); 2: in = y1 -> y2; 3: in = y2 -> y3; 4: in = y3 -> y (in place)
+        for (int stage = 1; stage <= 4; stage++) {
+          const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
+          LbStage sg;
+          sg.in = P.bufs[stage - 1];
+          sg.y = P.bufs[0];
+          sg.y1 = P.bufs[1];
+          sg.y2 = P.bufs[2];
+          sg.out = stage == 4 ? P.bufs[0] : P.bufs[stage];
+          sg.stage = stage;
+          sg.h = h_piece;
+          lindblad_stage_kernel<<<grid_pairs, 512, smem_stage, P.st>>>(P.a, P.lists, P.cu, set, sg);
+        }
       }
       pos += 2;
     }
     CASQ_CUDA(cudaGetLastError());
     pos += 1;
     if (g.out_keep[p + 1] && (rc = emit())) return rc;
+  }
+  for (int i = 0; i + 1 < n_parts; i++) {  // join
+    CASQ_CUDA(cudaEventRecord(m->ev_join[i], m->aux_stream[i]));
+    CASQ_CUDA(cudaStreamWaitEvent(st, m->ev_join[i], 0));
   }
   return CASQ_OK;
 }

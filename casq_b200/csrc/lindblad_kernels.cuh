@@ -22,6 +22,7 @@
 
 struct LbArgs {
   int d;
+  long long Bp, b0;  // stride of the parameter block (the whole batch) and first trajectory of this part of it
   int ld;  // row stride of the density-matrix buffers: d rounded up to 8 elements, so every row starts on a 128 B line
   long long B;
   int KA, NF, NTF, NQ, NU, NG, NP, W;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) lindblad_coef_kernel(const LbArgs a, long
   const long long entry = entry0 + set;
   if (tid == 0) {
     dcplx env[LB_MAXK];
-    casq_channel_envelopes<LB_MAXK>(a.slots, a.params, a.B, b, __ldg(a.idx + entry), env);
+    casq_channel_envelopes<LB_MAXK>(a.slots, a.params, a.Bp, a.b0 + b, __ldg(a.idx + entry), env);
 #pragma unroll
     for (int k = 0; k < LB_MAXK; k++) s_env[k] = env[k];
   }

@@ -267,6 +267,11 @@ extern "C" void casq_model_destroy(casq_model* m) {
   DeviceBuf* bufs[] = {&m->tab, &m->tab_idx, &m->tab_times, &m->pieces_n, &m->pieces_h, &m->consts,
                        &m->work0, &m->work1, &m->work2, &m->work3};
   for (DeviceBuf* b : bufs) b->release();
+  for (int i = 0; i < 3; i++) {
+    if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);
+    if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   delete m;
 }
 
