@@ -14,7 +14,8 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2
 ncu --set full --clock-control none --import-source on -k regex:sv_rk4_small -s 3 -c 1 -o gpurun_out/prof_rk4 -f \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 python scripts/gpu_time_lindblad.py 64 > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"lindblad_stage|lindblad_coef" -s 210 -c 5 -o gpurun_out/prof_lindblad -f \
+CASQ_LB_PARTS=1 python scripts/gpu_time_lindblad.py 64 > gpurun_out/plain3b.log 2>&1 &&
+CASQ_LB_PARTS=1 ncu --set full --clock-control none --import-source on -k regex:"lindblad_stage|lindblad_coef" -s 210 -c 5 -o gpurun_out/prof_lindblad -f \
     python scripts/gpu_time_lindblad.py 64 > gpurun_out/ncu_lb.log 2>&1
 python scripts/gpu_time_expm.py > gpurun_out/plain4.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:propagator_expm -c 1 -o gpurun_out/prof_expm -f \
