@@ -166,3 +166,25 @@ def test_decorators_and_per_qubit_populations(caplog):
     assert two == pytest.approx(O.populations_dict(np.full(9, 1 / 9), subsystem_dims=[3, 3], measured=(0, 1)))
     one = populations_by_qubit(np.array([0.5, 0.25, 0.25, 0, 0, 0, 0, 0, 0]), [3, 3], measured=[0])
     assert one == pytest.approx({"0": 0.5, "1": 0.5})
+
+
+def test_measurement_script_problems_equal_the_oracle_definitions():
+    """scripts/ builds its benchmark problems with the PRODUCT's models (it must not import the oracle); they have to be the
+    same problems the parity tests define through the oracle: bit-equal operators, channels, carriers and dt."""
+    import oracle as O
+    from scripts import _problems as P
+    assert P.DT == O.MANILA_DT and P.CARRIERS == O.MANILA_CARRIERS
+    for eq in ([0], [0, 1], None):
+        a, b = P.manila(eq), O.parse_hamiltonian_dict(O.MANILA, eq)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == list(b[2])
+    v = O.MANILA["vars"]
+    for nq in (2, 3):
+        qm = {q: (v[f"wq{q}"], v[f"delta{q}"], v[f"omegad{q}"]) for q in range(nq)}
+        cm = {(q, q + 1): v[f"jq{q}q{q + 1}"] for q in range(nq - 1)}
+        b = O.parse_hamiltonian_dict(O.transmon_hamiltonian_dict(qm, cm), None)
+        a = P.chain(nq)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == list(b[2])
+    import pathlib
+    for f in pathlib.Path(P.__file__).parent.glob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f.name
