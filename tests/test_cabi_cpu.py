@@ -95,3 +95,26 @@ def test_dissipators_accepted(native_lib):
     m.set_dissipators(np.array([a * 100.0, a.T @ a * 50.0]))
     with pytest.raises(Exception):
         m.set_dissipators(np.zeros((1, 2, 2)))
+
+
+def test_solver_entry_points_validate_arguments_before_touching_the_gpu(native_lib):
+    """Every solver entry point rejects a NULL handle / inconsistent arguments with a status and a message (no CUDA call
+    is needed for that, so this runs on the CPU box); B = 0 is a successful no-op."""
+    L = native_lib
+    assert L.casq_solve_sv_rk4(None, 0, None, 0, None, None, 0, 0.0, 1.0, 0.1, 2, None, None, None) == -1
+    assert b"NULL model" in L.casq_last_error()
+    assert L.casq_solve_sv_dopri5(None, 0, None, 0, None, None, 0, 0.0, 1.0, 1e-6, 1e-6, 0.0, 0, 2, None, None, None, None, None) == -1
+    assert b"NULL model" in L.casq_last_error()
+    assert L.casq_propagators_expm(None, 0, None, 0, None, 0.0, 1.0, 0.1, None, None) == -1
+    assert b"NULL model" in L.casq_last_error()
+    assert L.casq_solve_lindblad_rk4(None, 0, None, 0, None, None, 0, 0.0, 1.0, 0.1, 2, None, None, None, None) == -1
+    assert b"NULL model" in L.casq_last_error()
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    m = _native.NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], O.MANILA_DT, rotating_frame=st)
+    h = m.handle
+    # reversed time span and negative batch are caught before any launch; an empty batch succeeds
+    assert L.casq_solve_sv_rk4(h, 0, None, 4, None, None, 0, 1.0, 0.0, 0.1, 2, None, None, None) < 0
+    assert L.casq_solve_sv_dopri5(h, 0, None, -1, None, None, 0, 0.0, 1.0, 1e-6, 1e-6, 0.0, 0, 2, None, None, None, None, None) < 0
+    assert b"negative" in L.casq_last_error()
+    assert L.casq_propagators_expm(h, 0, None, 0, None, 0.0, 1e-9, 1e-10, None, None) == 0
+    m.close()
