@@ -254,6 +254,128 @@ __device__ __forceinline__ void wsolve9(int lane, double2* Q, double2* Pm) {
   __syncwarp();
 }
 
+// d = 9 product with the output tile (row i, columns j0..j0+2) left in REGISTERS; lanes >= 27 idle.
+__device__ __forceinline__ void mm9_tile(int lane, const double2* X, const double2* Y, double2 (&t)[3]) {
+  t[0] = t[1] = t[2] = make_double2(0.0, 0.0);
+  if (lane < 27) {
+    const int i = lane / 3, j0 = 3 * (lane - 3 * i);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const double2 x = X[i * 9 + k];
+      t[0] = cfma(x, Y[k * 9 + j0], t[0]);
+      t[1] = cfma(x, Y[k * 9 + j0 + 1], t[1]);
+      t[2] = cfma(x, Y[k * 9 + j0 + 2], t[2]);
+    }
+  }
+}
+__device__ __forceinline__ void st9_tile(int lane, double2* C, const double2 (&t)[3]) {
+  if (lane < 27) {
+    const int i = lane / 3, j0 = 3 * (lane - 3 * i);
+    C[i * 9 + j0] = t[0];
+    C[i * 9 + j0 + 1] = t[1];
+    C[i * 9 + j0 + 2] = t[2];
+  }
+}
+
+// d = 9 version of wexpm with the element-wise passes fused into the product epilogues: the Pade polynomials are
+// accumulated from the power tiles while they are still in registers (A^4 / A^8 are never stored, V never leaves the
+// registers), and Q = V - U, P = V + U are formed from the U tile.  The kernel is bound by the shared-memory data pipe
+// (L1TEX 90 %): per step this removes 9 STS.128 and 12 LDS.128 per lane.
+__device__ double2* wexpm9(int lane, double2* A, double2* X1, double2* X2, double2* X3, double2* X4) {
+  for (int e = lane; e < 81; e += 32) X4[e].x = sqrt(A[e].x * A[e].x + A[e].y * A[e].y);
+  __syncwarp();
+  double nrm = 0.0;
+  if (lane < 9) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) s += X4[i * 9 + lane].x;
+    nrm = s;
+  }
+  for (int o = 16; o > 0; o >>= 1) nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, o));
+  __syncwarp();
+  int mi, s = 0;  // Pade order m = 3 + 2 mi
+  if (nrm < 1.495585217958292e-2)
+    mi = 0;
+  else if (nrm < 2.539398330063230e-1)
+    mi = 1;
+  else if (nrm < 9.504178996162932e-1)
+    mi = 2;
+  else {
+    mi = 3;
+    const double r = nrm / 2.097847961257068e0;
+    s = r > 1.0 ? (int)ceil(log2(r)) : 0;
+    if (s > 0) {
+      const double sc = ldexp(1.0, -s);
+      for (int e = lane; e < 81; e += 32) A[e] = make_double2(A[e].x * sc, A[e].y * sc);
+      __syncwarp();
+    }
+  }
+  const double B3[4] = {120., 60., 12., 1.};
+  const double B5[6] = {30240., 15120., 3360., 420., 30., 1.};
+  const double B7[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+  const double B9[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.};
+  auto bc = [&](int k) { return mi == 0 ? B3[k] : (mi == 1 ? B5[k] : (mi == 2 ? B7[k] : B9[k])); };
+  const int i = lane / 3, j0 = 3 * (lane - 3 * i);
+  double2 t[3], od[3], vm[3];
+  mm9_tile(lane, A, A, t);  // A^2
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const double dg = (i == j0 + c) ? 1.0 : 0.0;
+    od[c] = make_double2(fma(bc(3), t[c].x, bc(1) * dg), bc(3) * t[c].y);
+    vm[c] = make_double2(fma(bc(2), t[c].x, bc(0) * dg), bc(2) * t[c].y);
+  }
+  if (mi >= 1) {
+    st9_tile(lane, X1, t);
+    __syncwarp();
+    mm9_tile(lane, X1, X1, t);  // A^4
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      od[c] = make_double2(fma(bc(5), t[c].x, od[c].x), fma(bc(5), t[c].y, od[c].y));
+      vm[c] = make_double2(fma(bc(4), t[c].x, vm[c].x), fma(bc(4), t[c].y, vm[c].y));
+    }
+    if (mi >= 2) {
+      st9_tile(lane, X2, t);
+      __syncwarp();
+      mm9_tile(lane, X2, X1, t);  // A^6
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        od[c] = make_double2(fma(bc(7), t[c].x, od[c].x), fma(bc(7), t[c].y, od[c].y));
+        vm[c] = make_double2(fma(bc(6), t[c].x, vm[c].x), fma(bc(6), t[c].y, vm[c].y));
+      }
+      if (mi >= 3) {
+        st9_tile(lane, X3, t);
+        __syncwarp();
+        mm9_tile(lane, X3, X1, t);  // A^8
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          od[c] = make_double2(fma(bc(9), t[c].x, od[c].x), fma(bc(9), t[c].y, od[c].y));
+          vm[c] = make_double2(fma(bc(8), t[c].x, vm[c].x), fma(bc(8), t[c].y, vm[c].y));
+        }
+      }
+    }
+  }
+  st9_tile(lane, X4, od);  // the |A| scratch is free; X4 holds the odd polynomial
+  __syncwarp();            // also: every lane is done with X1 / X2 / X3 as operands
+  mm9_tile(lane, A, X4, t);  // U
+  if (lane < 27) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      X3[i * 9 + j0 + c] = make_double2(vm[c].x - t[c].x, vm[c].y - t[c].y);  // Q
+      X1[i * 9 + j0 + c] = make_double2(vm[c].x + t[c].x, vm[c].y + t[c].y);  // P
+    }
+  }
+  __syncwarp();
+  wsolve9(lane, X3, X1);
+  double2 *E = X1, *Sq = X2;
+  for (int q = 0; q < s; q++) {
+    wmatmul<9>(9, lane, Sq, E, E);
+    double2* tmp = E;
+    E = Sq;
+    Sq = tmp;
+  }
+  return E;
+}
+
 // expm(A) with FOUR work matrices X1..X4 (d*d each); A is overwritten (scaled); returns the buffer holding the result
 // (X1 or X2).  Orders 3/5/7/9 by Higham's theta_m; above theta_9 the matrix is scaled down to theta_9 and squared back.
 // (Higham switches to [13/13] with theta_13 there: same backward-error bound, but it needs three more live matrices.
@@ -378,7 +500,7 @@ __global__ void __launch_bounds__(32 * PROP_WARPS, DT == 9 ? 7 : 1) propagator_e
       prop_signals(a, b, pm, zr, zi);
       prop_assemble<DT>(a, d, pm, zr, zi, h, A, lane, 32);
       __syncwarp();
-      double2* E = wexpm<DT>(d, lane, A, X1, X2, X3, X4);
+      double2* E = DT == 9 ? wexpm9(lane, A, X1, X2, X3, X4) : wexpm<DT>(d, lane, A, X1, X2, X3, X4);
       wmatmul<DT>(d, lane, X4, E, Uacc);  // X4 is free once the odd polynomial has been consumed
       double2* t = Uacc;
       Uacc = X4;
