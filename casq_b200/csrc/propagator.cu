@@ -254,6 +254,62 @@ __device__ __forceinline__ void wsolve9(int lane, double2* Q, double2* Pm) {
   __syncwarp();
 }
 
+// wsolve9 with the operands already in registers in the PRODUCT layout: lane (row i, column block tj) holds
+// Q[i][3tj..3tj+2] and P[i][3tj..3tj+2], i.e. columns {3tj..} and {9+3tj..} of the augmented matrix, so Q = V - U and
+// P = V + U go from the product epilogue into the elimination without a round trip through shared memory.
+// scratch: 27 double2 (pivot row [18] + factors [9]); the solution is written to Eout (9x9).
+__device__ __forceinline__ void wsolve9_tiles(int lane, double2 (&q)[3], double2 (&p)[3], double2* scratch, double2* Eout) {
+  const int i = lane / 3, tj = lane - 3 * i;
+  const bool act = lane < 27;
+  double2* s_row = scratch;
+  double2* s_f = scratch + 18;
+  int myk = -1;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const int kb = k / 3, kt = k % 3;
+    const double2 x = q[kt];
+    unsigned key = 0;
+    if (act && tj == kb && myk < 0) key = ((unsigned)__double2hiint(x.x * x.x + x.y * x.y) & 0xFFFFFFF0u) | (unsigned)(15 - i);
+    key = __reduce_max_sync(0xffffffffu, key);
+    const int pr = 15 - (int)(key & 15u);
+    const double px = __shfl_sync(0xffffffffu, x.x, 3 * pr + kb), py = __shfl_sync(0xffffffffu, x.y, 3 * pr + kb);
+    const double inv_n = 1.0 / (px * px + py * py);
+    const double2 pinv = make_double2(px * inv_n, -py * inv_n);
+    if (act) {
+      if (i == pr) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          q[c] = cmul(q[c], pinv);
+          p[c] = cmul(p[c], pinv);
+          s_row[3 * tj + c] = q[c];
+          s_row[9 + 3 * tj + c] = p[c];
+        }
+        myk = k;
+      } else if (tj == kb) {
+        s_f[i] = x;
+      }
+    }
+    __syncwarp();
+    if (act && i != pr) {
+      const double2 f = s_f[i];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double2 rq = s_row[3 * tj + c], rp = s_row[9 + 3 * tj + c];
+        q[c].x = fma(-f.x, rq.x, fma(f.y, rq.y, q[c].x));
+        q[c].y = fma(-f.x, rq.y, fma(-f.y, rq.x, q[c].y));
+        p[c].x = fma(-f.x, rp.x, fma(f.y, rp.y, p[c].x));
+        p[c].y = fma(-f.x, rp.y, fma(-f.y, rp.x, p[c].y));
+      }
+    }
+    __syncwarp();
+  }
+  if (act) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) Eout[myk * 9 + 3 * tj + c] = p[c];
+  }
+  __syncwarp();
+}
+
 // d = 9 product with the output tile (row i, columns j0..j0+2) left in REGISTERS; lanes >= 27 idle.
 __device__ __forceinline__ void mm9_tile(int lane, const double2* X, const double2* Y, double2 (&t)[3]) {
   t[0] = t[1] = t[2] = make_double2(0.0, 0.0);
@@ -357,15 +413,13 @@ __device__ double2* wexpm9(int lane, double2* A, double2* X1, double2* X2, doubl
   st9_tile(lane, X4, od);  // the |A| scratch is free; X4 holds the odd polynomial
   __syncwarp();            // also: every lane is done with X1 / X2 / X3 as operands
   mm9_tile(lane, A, X4, t);  // U
-  if (lane < 27) {
+  double2 qq[3], pp[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      X3[i * 9 + j0 + c] = make_double2(vm[c].x - t[c].x, vm[c].y - t[c].y);  // Q
-      X1[i * 9 + j0 + c] = make_double2(vm[c].x + t[c].x, vm[c].y + t[c].y);  // P
-    }
+  for (int c = 0; c < 3; c++) {
+    qq[c] = make_double2(vm[c].x - t[c].x, vm[c].y - t[c].y);  // Q = V - U
+    pp[c] = make_double2(vm[c].x + t[c].x, vm[c].y + t[c].y);  // P = V + U
   }
-  __syncwarp();
-  wsolve9(lane, X3, X1);
+  wsolve9_tiles(lane, qq, pp, X3, X1);  // X3: scratch (A^6 is dead); solution -> X1 (A^2 is dead)
   double2 *E = X1, *Sq = X2;
   for (int q = 0; q < s; q++) {
     wmatmul<9>(9, lane, Sq, E, E);
