@@ -381,7 +381,9 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
     long long b0, Bc;
     cudaStream_t st;
   };
-  int n_parts = (int)std::min<long long>(4, std::max<long long>(1, B / 16));  // measured at d = 243, B = 128: 161 / 178 / 183 / 184 traj/s for 1 / 2 / 3 / 4 parts
+  // measured at d = 243: B = 128: 161 / 178 / 183 / 184 traj/s for 1 / 2 / 3 / 4 parts; B = 16: 84 / 95 / - / 97.  Small
+  // matrices (a stage is a few microseconds) stay on one stream: four times the launches would only add host time.
+  int n_parts = d >= 64 ? (int)std::min<long long>(4, std::max<long long>(1, B / 4)) : 1;
   if (const char* e = getenv("CASQ_LB_PARTS")) n_parts = std::min(4, std::max(1, atoi(e)));  // tuning knob
   n_parts = (int)std::min<long long>(n_parts, B);
   if (n_parts > 1 && !m->ev_fork) CASQ_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
