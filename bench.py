@@ -69,8 +69,8 @@ def workload_config(n_gpus: int) -> dict:
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_oracle_points(indices, rank=0):
-    """Single-point oracle solves (what casq does per sweep point).  Returns seconds taken."""
+def cpu_oracle_points(indices, rank=0, want_states=False):
+    """Single-point oracle solves (what casq does per sweep point).  Returns seconds taken (and the final states)."""
     import oracle as O
 
     st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
@@ -78,11 +78,13 @@ def cpu_oracle_points(indices, rank=0):
     p = sweep_params(rank)
     y0 = np.array([1, 0, 0], dtype=complex)
     t0 = time.perf_counter()
+    states = []
     for i in indices:
         samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", DURATION)],
                                     [dict(amp=p["amp"][i], angle=0.0, sigma=p["sigma"], beta=p["beta"][i])])
-        O.rk4_solve(model, samples, y0, (0.0, T_FINAL_SAMPLES * DT), DT / SUBSTEPS)
-    return time.perf_counter() - t0
+        states.append(O.rk4_solve(model, samples, y0, (0.0, T_FINAL_SAMPLES * DT), DT / SUBSTEPS)[1][0, -1])
+    sec = time.perf_counter() - t0
+    return (sec, np.array(states)) if want_states else sec
 
 
 def _cpu_worker(args):
@@ -97,6 +99,19 @@ def run_reference(args) -> None:
         return
     import multiprocessing as mp
 
+    # The real reference (casq + qiskit-dynamics 0.4.1) is tried first; neither this image nor its offline wheelhouse
+    # carries qiskit / qiskit-dynamics / jax and casq's build backend (poetry-core) is absent too
+    # (profiles/r02_reference_install.log), so the arm falls back to the oracle port and says so.
+    ref_error = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import qiskit_dynamics  # noqa: F401
+        from casq.backends.qiskit.qiskit_pulse_backend import QiskitPulseBackend  # noqa: F401
+        ref_error = "importable, but no timing harness is wired for it"  # pragma: no cover - never reached on this image
+    except Exception as e:  # noqa: BLE001
+        ref_error = f"{type(e).__name__}: {e}"
+    finally:
+        sys.path.pop(0)
     cores = os.cpu_count() or 1
     per_step = cores  # one single-point solve per core per step
     rng = np.random.default_rng(20260101)
@@ -117,11 +132,215 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": "trajectories/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample,
+                         "real_reference": ref_error},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs 3, 4, 5 measured in the same run; cfg 1 is the CPU-reference sanity case and lives in
+# tests/test_gpu_full_size.py.  Each returns {value, unit, ms, B_per_gpu, roofline{...}, cpu_baseline, max_err}.
+HBM_FALLBACK_GBS = 6554.6  # B200_PROFILING.md fallback = this pool's measured copy bandwidth
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (MEASURED_PEAKS.json absent)"
+
+
+def cfg3_problem(rank):
+    ww, aa = np.meshgrid(np.linspace(0, 768, 64), np.linspace(0.05, 0.8, 64), indexing="ij")
+    return dict(amp=aa.ravel(), angle=0.0, sigma=64.0 + rank, width=ww.ravel())
+
+
+def cfg4_problem(rank, B):
+    # BASELINE cfg 4: a in linspace(0.05, 0.5, 1024), 128 per GPU: rank r takes the r-th block of 128
+    return dict(amp=np.linspace(0.05, 0.5, 1024)[(rank % 8) * B:(rank % 8) * B + B], angle=0.0, sigma=64.0, beta=1.0)
+
+
+def cfg5_problem(rank, B):
+    rng = np.random.default_rng(20260101 + rank)
+    return dict(amp=0.12, angle=0.0, sigma=rng.uniform(16, 128, B), beta=rng.uniform(-4, 4, B))
+
+
+def _t1t2_ops(nq, T1=100e-6, T2=80e-6):
+    a = np.diag(np.sqrt(np.arange(1, 3)), k=1).astype(complex)
+    n = a.conj().T @ a
+    out = []
+    for q in range(nq):
+        def emb(m_):
+            full = np.array([[1.0 + 0j]])
+            for s in range(nq):
+                full = np.kron(m_ if s == q else np.eye(3), full)
+            return full
+        out += [np.sqrt(1 / T1) * emb(a), np.sqrt(2 * (1 / T2 - 1 / (2 * T1))) * emb(n)]
+    return np.array(out)
+
+
+def cpu_cfg3(points):
+    """Oracle exponential-midpoint propagators (scipy expm per step) for `points` of the cfg 3 grid -> (sec, U)."""
+    import oracle as O
+
+    v = O.MANILA["vars"]
+    hd = O.transmon_hamiltonian_dict({0: (v["wq0"], v["delta0"], v["omegad0"]), 1: (v["wq1"], v["delta1"], v["omegad1"])},
+                                     {(0, 1): v["jq0q1"]})
+    st, ops, ch, _ = O.parse_hamiltonian_dict(hd, None)
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st, rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"])
+    p = cfg3_problem(0)
+    t0 = time.perf_counter()
+    out = []
+    for i in points:
+        samples = O.channel_samples(ch, [O.PulseSpec("gaussian_square", "u0", 1024)],
+                                    [dict(amp=p["amp"][i], angle=0.0, sigma=p["sigma"], width=p["width"][i])])
+        out.append(O.expm_midpoint_propagators(om, samples, (0.0, 1024 * DT), DT)[0])
+    return time.perf_counter() - t0, np.array(out)
+
+
+def cpu_cfg4(n_samples):
+    """Oracle dense Lindblad RK4 on ONE cfg 4 trajectory over the first `n_samples` pulse samples (4 steps each)."""
+    import oracle as O
+
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, None)
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=np.diag(st).real,
+                       rwa_cutoff_freq=0.75 * O.MANILA_CARRIERS["d0"], dissipators=_t1t2_ops(5))
+    p = cfg4_problem(0, 128)
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", 256)], [dict(amp=p["amp"][-1:], angle=0.0, sigma=64.0, beta=1.0)])
+    rho0 = np.zeros((243, 243), dtype=complex)
+    rho0[0, 0] = 1
+    t0 = time.perf_counter()
+    rho = O.lindblad_rk4_solve(om, samples, rho0, (0.0, n_samples * DT), DT / 4)[1][0, -1]
+    return time.perf_counter() - t0, rho
+
+
+def cpu_cfg5(points):
+    import oracle as O
+
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st)
+    p = cfg5_problem(0, 10000)
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", 256)],
+                                [dict(amp=0.12, angle=0.0, sigma=p["sigma"][points], beta=p["beta"][points])])
+    t0 = time.perf_counter()
+    y = O.dopri5_jax_solve(om, samples, np.array([1, 0, 0]), (0.0, 256 * DT), rtol=1e-8, atol=1e-6, hmax=DT)[1][:, -1]
+    return time.perf_counter() - t0, y
+
+
+def run_configs(ctx) -> dict:
+    """cfg 3 / 4 / 5 on this rank's shard; results gathered to rank 0 with casq_b200.distributed.gather_batch inside the
+    timed region.  ctx: torch, dist, dev, rank, world, timed(fn, k), max_over_ranks, fp64_peak, cpu (bool)."""
+    torch, dev, rank, world = ctx["torch"], ctx["dev"], ctx["rank"], ctx["world"]
+    from casq_b200 import engine
+    from casq_b200.distributed import gather_batch
+    from scripts import _problems as P
+
+    res = {}
+    reps = 2
+    # ---------------- cfg 3: 2 transmons (d = 9), GaussianSquare on u0, 64 x 64 sweep, one expm per sample (RWA)
+    st2, ops2, ch2 = P.chain(2)
+    nm2 = P.native(st2, ops2, ch2, rwa=0.75 * P.CARRIERS["d0"], device=dev.index)
+    B3 = 4096
+    p3 = engine.pack_params([cfg3_problem(rank)], device=dev)
+    sl3 = [("gaussian_square", ch2.index("u0"), 0, 1024)]
+    keep = {}
+
+    def run3():
+        keep["U"] = engine.propagators_expm(nm2, sl3, p3, (0.0, 1024 * DT), DT)
+        keep["all"] = gather_batch(keep["U"], B3 * world, dst=0)
+
+    ms = ctx["max_over_ranks"](ctx["timed"](run3, reps, warm=1))
+    U = keep["U"]
+    unit = float((U.conj().transpose(1, 2) @ U - torch.eye(9, device=dev, dtype=U.dtype)).abs().max())
+    flop3 = 6.0e4 * 1024 * B3  # SURVEY 8(d): F_expm(9, s=2) ~ 6.0e4 flop per step (Pade-13 count; the kernel runs orders 3-9)
+    r3 = {"workload": "cfg3: 2 transmons d=9, GaussianSquare(1024) on u0, 64x64 (amp,width) points per GPU, expm-midpoint, "
+                      "1024 steps, RWA 0.75 d0", "B_per_gpu": B3, "steps": 1024, "value": B3 * world / (ms * 1e-3),
+          "unit": "unitaries/s", "ms": ms, "max_unitarity_defect": unit,
+          "roofline": {"bound": "fp64", "achieved": flop3 / (ms * 1e-3) / 1e12, "peak": ctx["fp64_peak"], "unit": "TFLOP/s",
+                       "frac": flop3 / (ms * 1e-3) / 1e12 / ctx["fp64_peak"] if ctx["fp64_peak"] else None, "traffic": None,
+                       "flop_per_step_model": 6.0e4, "kernel": "propagator_expm_kernel<9>"}}
+    if ctx["cpu"]:
+        pts = [0, 1365, 2730, 4095]
+        sec, Uo = cpu_cfg3(pts)
+        r3["cpu_baseline"] = {"value": len(pts) / sec, "unit": "unitaries/s", "cores": 1, "kind": "port",
+                              "sample": f"{len(pts)} points of the grid, 1024 scipy-expm steps each"}
+        r3["max_err"] = float(np.abs(U[pts].cpu().numpy() - Uo).max())
+    res["cfg3"] = r3
+    del keep, U
+    # ---------------- cfg 5: 1e4 DRAG candidates per GPU, adaptive Dopri5 (atol 1e-6, rtol 1e-8, hmax dt)
+    st1, ops1, ch1 = P.manila([0])
+    nm1 = P.native(st1, ops1, ch1, device=dev.index)
+    B5 = 10000
+    prob5 = cfg5_problem(rank, B5)
+    p5 = engine.pack_params([prob5], device=dev)
+    y0 = np.array([1, 0, 0])
+    keep = {}
+
+    def run5():
+        keep["r"] = engine.solve_sv_dopri5(nm1, [("drag", 0, 0, 256)], p5, y0, (0.0, 256 * DT), rtol=1e-8, atol=1e-6, hmax=DT,
+                                           return_stats=True)
+        keep["all"] = gather_batch(keep["r"][0][:, -1], B5 * world, dst=0)
+
+    ms = ctx["max_over_ranks"](ctx["timed"](run5, 3, warm=1))
+    y5, ns5, st5 = keep["r"]
+    att = int(ns5[:, 0].sum())
+    flop5 = 1152.0 * att  # SURVEY 8(d): F_step^{DP5} = 1152 flop per ATTEMPTED step, counted by the kernel
+    _, probs, pops = engine.postprocess_sv(nm1, np.array([0.0, 256 * DT]), y5)
+    r5 = {"workload": "cfg5: 1e4 DragPulseGate(256, amp 0.12) candidates per GPU, (sigma,beta)~U[16,128]xU[-4,4], Dopri5 "
+                      "atol 1e-6 rtol 1e-8 hmax dt", "B_per_gpu": B5, "value": B5 * world / (ms * 1e-3), "unit": "trajectories/s",
+          "ms": ms, "attempted_steps": att, "accepted_steps": int(ns5[:, 1].sum()), "failed": int((st5 != 0).sum()),
+          "best_infidelity_1_minus_P1": float((1 - pops[:, -1, 1]).min()),
+          "roofline": {"bound": "fp64", "achieved": flop5 / (ms * 1e-3) / 1e12, "peak": ctx["fp64_peak"], "unit": "TFLOP/s",
+                       "frac": flop5 / (ms * 1e-3) / 1e12 / ctx["fp64_peak"] if ctx["fp64_peak"] else None, "traffic": None,
+                       "flop_per_attempted_step": 1152, "kernel": "sv_dopri5_kernel<3,1>"}}
+    if ctx["cpu"]:
+        pts = np.arange(0, B5, B5 // 12)[:12]
+        sec, yo = cpu_cfg5(pts)
+        r5["cpu_baseline"] = {"value": len(pts) / sec, "unit": "trajectories/s", "cores": 1, "kind": "port",
+                              "sample": f"{len(pts)} candidates, single-point jax-odeint restatement in a Python loop"}
+        r5["max_err"] = float(np.abs(y5[torch.as_tensor(pts, device=dev), -1].cpu().numpy() - yo).max())
+    res["cfg5"] = r5
+    del keep
+    # ---------------- cfg 4: 5 transmons (d = 243), T1/T2 Lindblad, RK4 dt/4 (S = 1028), 128 density matrices per GPU
+    st5m, ops5, ch5 = P.manila(None)
+    nm5 = P.native(st5m, ops5, ch5, frame="diag", rwa=0.75 * P.CARRIERS["d0"], device=dev.index)
+    nm5.set_dissipators(P.t1t2(5))
+    B4 = 128
+    p4 = engine.pack_params([cfg4_problem(rank, B4)], device=dev)
+    rho0 = np.zeros(243, dtype=complex)
+    rho0[0] = 1
+    sl4 = [("drag", ch5.index("d0"), 0, 256)]
+    keep = {}
+
+    def run4():
+        keep["r"] = engine.solve_lindblad_rk4(nm5, sl4, p4, rho0, (0.0, 257 * DT), DT / 4, want_rho=False)
+        keep["all"] = gather_batch(keep["r"][1][:, -1], B4 * world, dst=0)  # observables only: 2 kB per point
+
+    ms = ctx["max_over_ranks"](ctx["timed"](run4, reps, warm=1))
+    pops = keep["r"][1][:, -1]
+    bytes4 = 8.0 * 243 * 243 * 16 * 1028 * B4  # SURVEY 8(d): 4 stages x (read rho + write k) = 7.558 MB per step
+    peak, src = _hbm_peak()
+    r4 = {"workload": "cfg4: full ibmq_manila d=243, T1=100us T2=80us per qubit, DRAG(256) on d0, RK4 max_dt=dt/4 (S=1028), "
+                      "RWA 0.75 d0, 128 density matrices per GPU", "B_per_gpu": B4, "steps": 1028,
+          "value": B4 * world / (ms * 1e-3), "unit": "trajectories/s", "ms": ms,
+          "trace_defect": float((pops.sum(-1) - 1).abs().max()),
+          "roofline": {"bound": "hbm", "achieved": bytes4 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": bytes4 / (ms * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_step_model": 7.558e6,
+                       "peak_source": src, "kernel": "lindblad stage kernels (4 launches per RK4 step)"}}
+    if ctx["cpu"]:
+        n_s = 12
+        sec, rho_o = cpu_cfg4(n_s)
+        rho_g, _ = engine.solve_lindblad_rk4(nm5, sl4, p4[:, :, -1:].contiguous(), rho0, (0.0, n_s * DT), DT / 4, want_pops=False)
+        r4["cpu_baseline"] = {"value": 1.0 / (sec * 1028 / (4 * n_s)), "unit": "trajectories/s", "cores": os.cpu_count(),
+                              "kind": "port", "sample": f"1 trajectory, first {4 * n_s} of 1028 RK4 steps (dense numpy, BLAS threads), "
+                                                         "scaled to the full step count"}
+        r4["max_err"] = float(np.abs(rho_g[0, -1].cpu().numpy() - rho_o).max())
+        r4["max_err_sample"] = f"rho after the first {4 * n_s} steps of the same trajectory"
+    res["cfg4"] = r4
+    return res
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -209,7 +428,7 @@ def run_ours(args) -> None:
     max_dt = DT / SUBSTEPS
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = torch.empty((B, 2, 3), dtype=torch.complex128, device=dev)
-    gathered = [torch.empty((B, 3, 2), dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    from casq_b200.distributed import gather_batch, shard_bounds
 
     def barrier():
         if world > 1:
@@ -227,10 +446,12 @@ def run_ours(args) -> None:
         """table kernel + RK4 kernel (+ the one result gather when sharded)."""
         model.invalidate_cache()
         engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
-        if world > 1:
-            dist.all_gather(gathered, torch.view_as_real(out[:, 1, :]).contiguous())
+        if world > 1:  # the one collective of the path: final states to rank 0 (the only consumer)
+            gather_batch(out[:, 1, :], B * world, dst=0)
 
-    def timed(fn, k):
+    def timed(fn, k, warm=0):
+        for _ in range(warm):
+            fn()
         tot = 0.0
         for _ in range(k):
             flush.fill_(1)
@@ -271,7 +492,7 @@ def run_ours(args) -> None:
         host_final.copy_(sol.states[:, -1, :], non_blocking=True)
         host_pops.copy_(sol.populations[:, -1, :], non_blocking=True)
         if world > 1:
-            dist.all_gather(gathered, torch.view_as_real(sol.states[:, -1, :]).contiguous())
+            gather_batch(sol.states[:, -1, :], B * world, dst=0)
         torch.cuda.current_stream(dev).synchronize()
 
     for _ in range(args.warmup):
@@ -282,15 +503,45 @@ def run_ours(args) -> None:
     h2d = host_params.numel() * 8
     d2h = host_final.numel() * 16 + host_pops.numel() * 8
 
-    fp64_peak = engine.fp64_fma_probe(local_rank) if rank == 0 else 0.0
+    # ---- strong scaling: the named 1e5-point grid split over the N GPUs (B/N points each), same timed region rules
+    strong = None
+    if world > 1:
+        lo, hi = shard_bounds(B, rank, world)
+        sp = sweep_params(0)
+        sub_params = engine.pack_params([dict(amp=sp["amp"][lo:hi], angle=0.0, sigma=SIGMA, beta=sp["beta"][lo:hi])], device=dev)
+        sub_out = torch.empty((hi - lo, 2, 3), dtype=torch.complex128, device=dev)
+
+        def strong_step():
+            model.invalidate_cache()
+            engine.solve_sv_rk4(model, slots, sub_params, y0, t_span, max_dt, out=sub_out)
+            gather_batch(sub_out[:, 1, :], B, dst=0)
+
+        barrier()
+        ms_strong = max_over_ranks(timed(strong_step, args.steps, warm=args.warmup))
+        barrier()
+        strong = {"global_points": B, "points_per_gpu": B // world, "ms_per_step": ms_strong, "value": B / (ms_strong * 1e-3),
+                  "unit": "trajectories/s", "scaling": "strong"}
+
+    fp64_peak = engine.fp64_fma_probe(local_rank)
     cpu = None
+    max_state_err = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = 12
         idx = np.random.default_rng(20260101).integers(0, B, size=n)
-        sec = cpu_oracle_points([int(i) for i in idx])
+        sec, want = cpu_oracle_points([int(i) for i in idx], want_states=True)
         cpu = {"value": n / sec, "unit": "trajectories/s", "cores": 1, "kind": "port",
                "sample": f"{n} random points of the cfg2 grid, single-point RK4 solves (S=10280) in a Python loop, 1 core "
                          f"of {os.cpu_count()}"}
+        engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
+        got = out[torch.as_tensor(idx, device=dev), 1, :].cpu().numpy()
+        max_state_err = {"value": float(np.abs(got - want).max()), "points": n, "against": "oracle port (same RK4 grid)",
+                         "bar": 1e-6}
+    configs = None
+    if not args.no_configs:
+        barrier()
+        configs = run_configs({"torch": torch, "dev": dev, "rank": rank, "world": world, "timed": timed,
+                               "max_over_ranks": max_over_ranks, "fp64_peak": fp64_peak,
+                               "cpu": rank == 0 and world == 1 and not args.no_cpu_baseline})
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -318,6 +569,9 @@ def run_ours(args) -> None:
                          "flop_per_step": FLOP_PER_STEP, "dense_model_flop_per_step": FLOP_PER_STEP_DENSE_MODEL,
                          "peak_source": "measured live: casq_fp64_fma_probe (MEASURED_PEAKS.json has no fp64 entry)"},
             "cpu_baseline": cpu,
+            "max_state_err": max_state_err,
+            "strong_scaling": strong,
+            "configs": configs,
             "clocks": clocks.summary(),
         }))
     if world > 1:
@@ -331,6 +585,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg 3/4/5 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,6 +74,8 @@ struct casq_model {
   DeviceBuf tab, tab_idx, tab_times, pieces_n, pieces_h, consts, work0, work1, work2, work3;
   // cache key of the table currently resident in `tab`
   std::string tab_key;
+  long long tab_NT = 0;   // shape of the cached fixed-step grid (small RK4 path)
+  int tab_n_pieces = 0;
   // second stream + fork/join events of the Lindblad path (several parts of the batch in flight fill each other's grid tails)
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};

@@ -705,12 +705,9 @@ static cudaError_t launch_small(const SmallArgs& a, cudaStream_t st) {
   const long long grid = (a.B + block - 1) / block;
   constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
   const size_t smem = 2 * (size_t)kEnt * Entry<D, KA, RWA, HAS_S, TRI>::W * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // the attribute is per device: set it on every call (a few hundred ns) rather than caching it per process
+  cudaError_t e = cudaFuncSetAttribute(sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   sv_rk4_small_kernel<D, KA, RWA, HAS_S, TRI><<<(unsigned)grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -771,45 +768,48 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
   const int NE = tri ? d - 1 : d * (d - 1) / 2;
   const int W = 2 * KA + (has_s ? 2 * NE : 0) + KA * NE * (m->rwa ? 4 : 2);
 
-  // --- time grid + table (cached on the handle)
-  TimeGrid g;
-  int rc = casq_build_time_grid(t0, t1, max_dt, T, t_eval, m->dt, n_total, &g);
-  if (rc != CASQ_OK) return rc;
-  const long long NT = (long long)g.times.size();
-  const int n_pieces = (int)g.piece_nsteps.size();
+  // --- time grid + table (cached on the handle: a cache hit does no O(S) host work)
   std::string key;
   {
-    char head[256];
-    snprintf(head, sizeof(head), "small|%d|%d|%d|%d|%d|%a|%a|%a|%d|%d|", d, KA, (int)has_s, (int)tri, (int)m->rwa, t0, t1,
-             max_dt, T, n_total);
+    char head[320];
+    snprintf(head, sizeof(head), "small|%d|%d|%d|%d|%d|%a|%a|%a|%d|%d|%p|", d, KA, (int)has_s, (int)tri, (int)m->rwa, t0, t1,
+             max_dt, T, n_total, (void*)st);
     key = head;
     for (int k = 0; k < KA; k++) key += std::to_string(active[k]) + ",";
     if (t_eval) key.append(reinterpret_cast<const char*>(t_eval), sizeof(double) * T);
   }
-  std::vector<char> keep(g.out_keep.begin(), g.out_keep.end());
-  // fast-step masks: simulate the envelope cache (cur) over the shared time grid
-  std::vector<unsigned> masks;
-  {
-    int cur = -2;
-    long long p0 = 0;
-    for (int p = 0; p < n_pieces; p++) {
-      const int n = g.piece_nsteps[p];
-      for (int s0 = 0; s0 < n; s0 += SMALL_CHUNK_STEPS) {
-        unsigned w = 0;
-        for (int s = s0; s < n && s < s0 + SMALL_CHUNK_STEPS; s++) {
-          const int ia = g.sample_idx[p0 + 2 * s], ib = g.sample_idx[p0 + 2 * s + 1], ic = g.sample_idx[p0 + 2 * s + 2];
-          if (ia == cur && ib == cur && ic == cur)
-            w |= 1u << (s - s0);
-          else
-            cur = ic;
-        }
-        masks.push_back(w);
-      }
-      p0 += 2LL * n + 1;
-    }
-  }
+  int rc;
   if (key != m->tab_key) {
     m->tab_key.clear();
+    TimeGrid g;
+    rc = casq_build_time_grid(t0, t1, max_dt, T, t_eval, m->dt, n_total, &g);
+    if (rc != CASQ_OK) return rc;
+    const long long NT = (long long)g.times.size();
+    const int n_pieces = (int)g.piece_nsteps.size();
+    std::vector<char> keep(g.out_keep.begin(), g.out_keep.end());
+    // fast-step masks: simulate the envelope cache (cur) over the shared time grid
+    std::vector<unsigned> masks;
+    {
+      int cur = -2;
+      long long p0 = 0;
+      for (int p = 0; p < n_pieces; p++) {
+        const int n = g.piece_nsteps[p];
+        for (int s0 = 0; s0 < n; s0 += SMALL_CHUNK_STEPS) {
+          unsigned w = 0;
+          for (int s = s0; s < n && s < s0 + SMALL_CHUNK_STEPS; s++) {
+            const int ia = g.sample_idx[p0 + 2 * s], ib = g.sample_idx[p0 + 2 * s + 1], ic = g.sample_idx[p0 + 2 * s + 2];
+            if (ia == cur && ib == cur && ic == cur)
+              w |= 1u << (s - s0);
+            else
+              cur = ic;
+          }
+          masks.push_back(w);
+        }
+        p0 += 2LL * n + 1;
+      }
+    }
+    m->tab_NT = NT;
+    m->tab_n_pieces = n_pieces;
     if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
     if ((rc = m->tab_idx.ensure(NT * sizeof(int)))) return rc;
     if ((rc = m->tab.ensure((size_t)NT * W * sizeof(double)))) return rc;
@@ -864,7 +864,7 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
   a.piece_n = (const int*)m->pieces_n.p;
   a.piece_h = (const double*)m->pieces_h.p;
   a.keep = (const char*)m->consts.p;
-  a.n_pieces = n_pieces;
+  a.n_pieces = m->tab_n_pieces;
   a.B = B;
   a.T = T;
   a.params = params_dev;
@@ -885,7 +885,7 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     }
   }
   a.identityU = m->U_is_identity ? 1 : 0;
-  a.NT = NT;
+  a.NT = m->tab_NT;
   a.fast_mask = (const unsigned*)m->work2.p;
   if ((rc = m->work3.ensure(sizeof(SmallArgs)))) return rc;
   a.self_dev = (const SmallArgs*)m->work3.p;

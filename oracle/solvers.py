@@ -274,12 +274,26 @@ def lindblad_rhs_dense(model: OracleModel, t, z, rho_fb):
     """
     H = model.hamiltonian_fb(t, z)  # [B,d,d]
     ph = np.exp(1j * model.bohr * t)
-    out = -1j * (H @ rho_fb - rho_fb @ H)
-    for L in model.diss_fb:
+    # (L(t)^+ L(t))_ab = e^{i(e_a-e_b)t} (L^+ L)_ab, so the anticommutator part needs one static matrix D = sum_j L_j^+ L_j:
+    #   rho' = A rho + rho A^+ + sum_j L_j(t) rho L_j(t)^+,   A = -i H_F(t) - 1/2 e^{i bohr t} o D
+    cache = getattr(model, "_lindblad_cache", None)
+    if cache is None:
+        D = sum(L.conj().T @ L for L in model.diss_fb)
+        diag_w = np.zeros_like(D)  # diagonal L_j: L rho L^+ is an elementwise product with l l^+
+        dense = []
+        for L in model.diss_fb:
+            if np.count_nonzero(L - np.diag(np.diag(L))) == 0:
+                l = np.diag(L)
+                diag_w = diag_w + np.outer(l, l.conj())
+            else:
+                dense.append(L)
+        cache = model._lindblad_cache = (D, diag_w, dense)
+    D, diag_w, dense = cache
+    A = -1j * H - 0.5 * (ph * D)
+    out = A @ rho_fb + rho_fb @ np.conj(np.swapaxes(A, -1, -2)) + diag_w * rho_fb
+    for L in dense:
         Lt = ph * L
-        Ld = Lt.conj().T
-        LdL = Ld @ Lt
-        out = out + Lt @ rho_fb @ Ld - 0.5 * (LdL @ rho_fb + rho_fb @ LdL)
+        out = out + Lt @ rho_fb @ Lt.conj().T
     return out
 
 

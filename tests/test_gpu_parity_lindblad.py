@@ -152,3 +152,80 @@ def test_lindblad_parts_on_several_streams_are_bit_identical(monkeypatch):
         out[parts] = (rho.clone(), pops.clone())
     for parts in ("3", "4"):
         assert torch.equal(out["1"][0], out[parts][0]) and torch.equal(out["1"][1], out[parts][1])
+
+
+def _chain_problem(qubits, t1t2_scale, rwa=True):
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, list(qubits))
+    Ls = _t1t2_ops(len(qubits), scale=t1t2_scale)
+    rf = np.diag(st).real
+    cut = 0.75 * O.MANILA_CARRIERS["d0"] if rwa else None
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=rf, rwa_cutoff_freq=cut, dissipators=Ls)
+    nm = NativeModel(st, ops, [O.MANILA_CARRIERS[c] for c in ch], DT, rotating_frame=rf, rwa_cutoff_freq=cut)
+    nm.set_dissipators(Ls)
+    return om, nm, ch
+
+
+def _random_density_matrices(rng, B, d, rank=3):
+    x = rng.normal(size=(B, d, rank)) + 1j * rng.normal(size=(B, d, rank))
+    rho = x @ np.conj(np.swapaxes(x, -1, -2))
+    return rho / np.trace(rho, axis1=-2, axis2=-1).real[:, None, None]
+
+
+@pytest.mark.parametrize("parts", ["1", "4"])
+@pytest.mark.parametrize("rho0_kind", ["ground", "random"])
+def test_lindblad_d81_off_diagonal_tile_pairs_vs_oracle(parts, rho0_kind, monkeypatch):
+    """Four transmons (d = 81): more than one tile per side, so the off-diagonal tile-pair path (left gathers of the
+    mirrored tile, transposed read, mirror store) is compared ELEMENT BY ELEMENT with the dense oracle -- 16 RK4 steps,
+    ragged batch, one and four stream parts, a random mixed rho0 so that every tile is non-zero from step 0, T1/T2 1e3 x
+    stronger so that the two-sided terms matter at 1e-9."""
+    monkeypatch.setenv("CASQ_LB_PARTS", parts)
+    rng = np.random.default_rng(81)
+    om, nm, ch = _chain_problem([0, 1, 2, 3], 1e3)
+    B, dur = 5, 8
+    p = dict(amp=rng.uniform(0.2, 0.9, B), angle=rng.uniform(-1, 1, B), sigma=3.0, beta=rng.uniform(-2, 2, B))
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p])
+    span = (0.0, 4 * DT)
+    te = np.array([0.0, 1.5, 4.0]) * DT
+    if rho0_kind == "ground":
+        rho0 = np.zeros((81, 81), dtype=complex)
+        rho0[0, 0] = 1
+        want = O.lindblad_rk4_solve(om, samples, rho0, span, DT / 4, te)[1]
+    else:
+        rho0 = _random_density_matrices(rng, B, 81)
+        want = np.concatenate([O.lindblad_rk4_solve(om, samples[b:b + 1], rho0[b], span, DT / 4, te)[1] for b in range(B)])
+    rho, pops = engine.solve_lindblad_rk4(nm, [("drag", ch.index("d0"), 0, dur)], engine.pack_params([p], device="cuda"), rho0,
+                                          span, DT / 4, te)
+    got = rho.cpu().numpy()
+    assert got.shape == (B, 3, 81, 81)
+    assert np.abs(got - want).max() < TOL_RHO
+    ref_pops = np.real(np.einsum("btii->bti", O.postprocess_density_matrices(om, te, want, normalize=False)))
+    assert np.abs(pops.cpu().numpy() - ref_pops).max() < TOL_RHO
+
+
+@pytest.mark.parametrize("scale,rho0_kind", [(1.0, "ground"), (1e3, "random")])
+def test_lindblad_d243_cfg4_operators_vs_oracle(scale, rho0_kind, monkeypatch):
+    """BASELINE cfg 4's own operators (full ibmq_manila, d = 243, RWA cutoff 0.75 d0, T1 = 100 us / T2 = 80 us per qubit,
+    DRAG on d0) against the dense oracle, element by element, for 20 RK4 steps: every one of the tile pairs of the
+    production kernel is exercised; the second case has a random mixed rho0 and 1e3 x faster T1/T2."""
+    rng = np.random.default_rng(243)
+    om, nm, ch = _chain_problem([0, 1, 2, 3, 4], scale)
+    B, dur = 2, 8
+    p = dict(amp=np.array([0.3, 0.85]), angle=np.array([0.0, 0.7]), sigma=3.0, beta=np.array([1.0, -2.0]))
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p])
+    span = (0.0, 5 * DT)
+    if rho0_kind == "ground":
+        rho0 = np.zeros((243, 243), dtype=complex)
+        rho0[0, 0] = 1
+        want = O.lindblad_rk4_solve(om, samples, rho0, span, DT / 4)[1]
+    else:
+        rho0 = _random_density_matrices(rng, B, 243)
+        want = np.concatenate([O.lindblad_rk4_solve(om, samples[b:b + 1], rho0[b], span, DT / 4)[1] for b in range(B)])
+    for parts in ("1", "2"):
+        monkeypatch.setenv("CASQ_LB_PARTS", parts)
+        rho, pops = engine.solve_lindblad_rk4(nm, [("drag", ch.index("d0"), 0, dur)], engine.pack_params([p], device="cuda"),
+                                              rho0, span, DT / 4)
+        got = rho.cpu().numpy()
+        assert np.abs(got - want).max() < TOL_RHO, parts
+        assert np.abs(got[:, -1] - np.conj(np.swapaxes(got[:, -1], -1, -2))).max() < 1e-13
+        ref_pops = np.real(np.einsum("btii->bti", O.postprocess_density_matrices(om, np.array(span), want, normalize=False)))
+        assert np.abs(pops.cpu().numpy() - ref_pops).max() < TOL_RHO
