@@ -29,6 +29,7 @@
 
 #include "lindblad_kernels.cuh"
 #include "lindblad_stage.cuh"
+#include "lindblad_chain.cuh"
 
 __global__ void sv_general_table_kernel(const double* __restrict__ times, long long NT, int KA, int d, int W,
                                         const double* __restrict__ two_pi_nu, const double* __restrict__ fe,
@@ -89,6 +90,414 @@ struct Builder {
     }
   }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Chain-of-three-level-sites detection (lindblad_chain.cuh).  Every element of A = -iH_F - D_F/2 and of the dissipators must
+// be (a) diagonal and time-independent, (b) a single-site ladder element x_q -> x_q +- 1, or (c) a nearest-neighbour
+// exchange element (x_q, x_q+1) -> (x_q -+ 1, x_q+1 +- 1), with value and time function depending only on the digits of the
+// sites it touches; each dissipator is either diagonal or a single-site ladder operator in one direction.
+struct ChainPlan {
+  bool ok = false;
+  int nq = 0;
+  unsigned drv_mask = 0;
+  int n2 = 0, two_q[LC_MAX2], two_dir[LC_MAX2];
+  int NS = 0, NC = 0, u_base = 0, w_base = 0;
+  std::vector<int> slot_start;
+  std::vector<cplx> atom_val;
+  std::vector<int> atom_code;
+  std::vector<cplx> G;  // [d*ld]
+};
+
+struct SlotRows {  // what each row contributes to one slot: (time-function code -> value)
+  std::map<int, std::map<int, cplx>> rows;
+  long long expected = 0;
+};
+
+static bool lc_classify(int nq, int r, int c, int* slot) {
+  // returns false when (r, c) is neither a single-site ladder element nor a nearest-neighbour exchange element
+  int qs[2], df[2], nd = 0, xr[LC_MAXQ];
+  int rr = r, cc = c;
+  for (int q = 0; q < nq; q++) {
+    const int a = rr % 3, b = cc % 3;
+    xr[q] = a;
+    rr /= 3;
+    cc /= 3;
+    if (a != b) {
+      if (nd == 2 || std::abs(b - a) != 1) return false;
+      qs[nd] = q;
+      df[nd] = b - a;
+      nd++;
+    }
+  }
+  if (nd == 1) {
+    const int q = qs[0];
+    *slot = df[0] > 0 ? (q * 2 + 0) * 2 + xr[q] : (q * 2 + 1) * 2 + xr[q] - 1;
+    return true;
+  }
+  if (nd == 2 && qs[1] == qs[0] + 1 && df[0] == -df[1]) {
+    const int q = qs[0];
+    const int jbase = 4 * nq;
+    if (df[0] < 0)  // c = r + 3^(q+1) - 3^q: n = x_q(r) - 1, m = x_(q+1)(r)
+      *slot = jbase + ((q * 2 + 0) * 2 + xr[q] - 1) * 2 + xr[q + 1];
+    else            // c = r - 3^(q+1) + 3^q: n = x_q(r), m = x_(q+1)(r) - 1
+      *slot = jbase + ((q * 2 + 1) * 2 + xr[q]) * 2 + xr[q + 1] - 1;
+    return true;
+  }
+  return false;
+}
+
+static bool lc_consistent(const SlotRows& sr, double tol, std::map<int, cplx>* rep) {
+  if (sr.rows.empty()) {
+    rep->clear();
+    return true;
+  }
+  if ((long long)sr.rows.size() != sr.expected) return false;  // some row that owns this slot has no element
+  const std::map<int, cplx>& first = sr.rows.begin()->second;
+  for (const auto& kv : sr.rows) {
+    if (kv.second.size() != first.size()) return false;
+    auto it = first.begin();
+    for (const auto& e : kv.second) {
+      if (e.first != it->first || std::abs(e.second - it->second) > tol * (1.0 + std::abs(it->second))) return false;
+      ++it;
+    }
+  }
+  *rep = first;
+  return true;
+}
+
+static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector<Atom>& one, int ld) {
+  ChainPlan P;
+  const int d = m->d;
+  int nq = 0, dd = 1;
+  while (dd < d) {
+    dd *= 3;
+    nq++;
+  }
+  if (dd != d || nq < 3 || nq > LC_MAXQ) return P;
+  if (getenv("CASQ_LB_GENERIC")) return P;  // test / tuning knob: force the generic shift-class kernel
+  P.nq = nq;
+  const int NX = 4 * nq, NJ = 8 * (nq - 1);
+  std::vector<SlotRows> slots(NX + NJ);
+  long long pw = 1;
+  for (int s = 0; s < NX; s++) slots[s].expected = d / 3;
+  for (int s = 0; s < NJ; s++) slots[NX + s].expected = d / 9;
+  (void)pw;
+  std::vector<cplx> adiag(d, cplx(0.0));
+  for (const Atom& at : one) {
+    const int code = bld.tf_id(at.sig, at.omega);
+    if (at.row == at.col) {
+      if (bld.tfs[code].first != 0 || bld.tfs[code].second != -1) return P;  // time-dependent diagonal element
+      adiag[at.row] += at.val;
+      continue;
+    }
+    int slot;
+    if (!lc_classify(nq, at.row, at.col, &slot)) return P;
+    slots[slot].rows[at.row][code] += at.val;
+  }
+  const double tol = 1e-12;
+  std::vector<std::map<int, cplx>> reps(NX + NJ);
+  for (int s = 0; s < NX + NJ; s++)
+    if (!lc_consistent(slots[s], tol, &reps[s])) return P;
+  for (int q = 0; q < nq; q++)
+    for (int k = 0; k < 4; k++)
+      if (!reps[q * 4 + k].empty()) P.drv_mask |= 1u << q;
+  // dissipators: diagonal ones go into G, single-site ladder ones become two-sided terms
+  std::vector<std::vector<cplx>> diagL;
+  std::vector<std::map<int, cplx>> ureps;
+  for (int j = 0; j < m->J; j++) {
+    const cplx* L = &m->Lfb[(size_t)j * d * d];
+    bool any_diag = false, any_off = false;
+    int q_ = -1, dir_ = 0;
+    SlotRows u[2];
+    u[0].expected = u[1].expected = d / 3;
+    for (int a_ = 0; a_ < d; a_++)
+      for (int b_ = 0; b_ < d; b_++) {
+        const cplx v = L[a_ * d + b_];
+        if (std::abs(v) == 0.0) continue;
+        if (a_ == b_) {
+          any_diag = true;
+          continue;
+        }
+        any_off = true;
+        int slot;
+        if (!lc_classify(nq, a_, b_, &slot) || slot >= NX) return P;
+        const int q = slot / 4, dirbit = (slot / 2) & 1, n = slot & 1;
+        const int dir = dirbit == 0 ? +1 : -1;
+        if (dir < 0) return P;  // raising-type dissipators (thermal excitation) run the generic kernel
+        if (q_ < 0) {
+          q_ = q;
+          dir_ = dir;
+        } else if (q_ != q || dir_ != dir) {
+          return P;
+        }
+        const int code = bld.tf_id(0, m->fe[a_] - m->fe[b_]);
+        u[n].rows[a_][code] += v;
+      }
+    if (any_diag && any_off) return P;
+    if (any_off) {
+      if (P.n2 >= LC_MAX2) return P;
+      std::map<int, cplx> r0, r1;
+      if (!lc_consistent(u[0], tol, &r0) || !lc_consistent(u[1], tol, &r1)) return P;
+      P.two_q[P.n2] = q_;
+      P.two_dir[P.n2] = dir_;
+      P.n2++;
+      ureps.push_back(r0);
+      ureps.push_back(r1);
+    } else if (any_diag) {
+      std::vector<cplx> l(d);
+      for (int a_ = 0; a_ < d; a_++) l[a_] = L[a_ * d + a_];
+      diagL.push_back(l);
+    }
+  }
+  // flatten the slots
+  P.u_base = NX + NJ;
+  P.NS = P.u_base + 2 * P.n2;
+  P.w_base = P.NS;
+  P.NC = P.NS + 4 * P.n2;
+  P.slot_start.push_back(0);
+  auto put = [&](const std::map<int, cplx>& rep) {
+    for (const auto& e : rep) {
+      P.atom_code.push_back(e.first);
+      P.atom_val.push_back(e.second);
+    }
+    P.slot_start.push_back((int)P.atom_code.size());
+  };
+  for (int s = 0; s < NX + NJ; s++) put(reps[s]);
+  for (const auto& r : ureps) put(r);
+  // G[r,c] = A_rr + conj(A_cc) + sum over diagonal L_j of l_j(r) conj(l_j(c))
+  P.G.assign((size_t)d * ld, cplx(0.0));
+  for (int r = 0; r < d; r++)
+    for (int c = 0; c < d; c++) {
+      cplx g = adiag[r] + std::conj(adiag[c]);
+      for (const auto& l : diagL) g += l[r] * std::conj(l[c]);
+      P.G[(size_t)r * ld + c] = g;
+    }
+  P.ok = true;
+  return P;
+}
+
+// The chain path: same buffers, time grid, stream parts and outputs as the generic path below; per RK4 step one small
+// coefficient kernel and four warp-per-tile-pair stage kernels (lindblad_chain.cuh).
+static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, int KA, const int* active, const DevSlots& ds,
+                              int n_total, int64_t B, const double* params_dev, const double* rho0_dev, int rho0_batched,
+                              double t0, double t1, double max_dt, int T, const double* t_eval, double* out_rho_dev,
+                              double* out_pops_dev, cudaStream_t st) {
+  const int d = m->d, ld = (d + 7) & ~7;
+  int rc;
+  TimeGrid g;
+  rc = casq_build_time_grid(t0, t1, max_dt, T, t_eval, m->dt, n_total, &g);
+  if (rc != CASQ_OK) return rc;
+  const long long NT = (long long)g.times.size();
+  const int NF = (int)bld.freqs.size(), NTF = (int)bld.tfs.size();
+  const int W = 2 * KA + 2 * NF;
+  m->tab_key.clear();
+  std::vector<double> consts(KA + std::max(NF, 1));
+  for (int k = 0; k < KA; k++) consts[k] = 2.0 * M_PI * m->nu[active[k]];
+  for (int f = 0; f < NF; f++) consts[KA + f] = bld.freqs[f];
+  std::vector<int> tf_sig(NTF), tf_freq(NTF);
+  for (int n = 0; n < NTF; n++) {
+    tf_sig[n] = bld.tfs[n].first;
+    tf_freq[n] = bld.tfs[n].second;
+  }
+  const int ntile = d / LC_T;
+  std::vector<int> pair_ij;
+  for (int I = 0; I < ntile; I++)  // pairs of one trajectory are adjacent tasks: its tiles stay hot in L2 / L1
+    for (int J = I; J < ntile; J++) {
+      pair_ij.push_back(I);
+      pair_ij.push_back(J);
+    }
+  const int npairs = (int)pair_ij.size() / 2;
+  auto align16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t off = 0;
+  const size_t o_tfsig = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
+  const size_t o_tffreq = off; off = align16(off + std::max(NTF, 1) * sizeof(int));
+  const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
+  const size_t o_ph = off; off = align16(off + (size_t)std::max(T, 1) * d * 16);
+  const size_t o_G = off; off = align16(off + (size_t)d * ld * 16);
+  const size_t o_pij = off; off = align16(off + pair_ij.size() * sizeof(int));
+  const size_t o_ss = off; off = align16(off + cp.slot_start.size() * sizeof(int));
+  const size_t o_av = off; off = align16(off + std::max<size_t>(cp.atom_val.size(), 1) * 16);
+  const size_t o_ac = off; off = align16(off + std::max<size_t>(cp.atom_code.size(), 1) * sizeof(int));
+  std::vector<unsigned char> blob(off, 0);
+  if (NTF) {
+    memcpy(&blob[o_tfsig], tf_sig.data(), NTF * sizeof(int));
+    memcpy(&blob[o_tffreq], tf_freq.data(), NTF * sizeof(int));
+  }
+  memcpy(&blob[o_V], m->V.data(), (size_t)d * d * 16);
+  {
+    cplx* ph = reinterpret_cast<cplx*>(&blob[o_ph]);
+    int slot = 0;
+    for (size_t i = 0; i < g.out_times.size() && slot < T; i++)
+      if (g.out_keep[i]) {
+        for (int e = 0; e < d; e++) ph[(size_t)slot * d + e] = std::polar(1.0, -m->fe[e] * g.out_times[i]);
+        slot++;
+      }
+  }
+  memcpy(&blob[o_G], cp.G.data(), (size_t)d * ld * 16);
+  memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
+  memcpy(&blob[o_ss], cp.slot_start.data(), cp.slot_start.size() * sizeof(int));
+  if (!cp.atom_val.empty()) {
+    memcpy(&blob[o_av], cp.atom_val.data(), cp.atom_val.size() * 16);
+    memcpy(&blob[o_ac], cp.atom_code.data(), cp.atom_code.size() * sizeof(int));
+  }
+  const size_t n_per = (size_t)d * d, n_pad = (size_t)d * ld;
+  if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
+  if ((rc = m->tab_idx.ensure(NT * sizeof(int)))) return rc;
+  if ((rc = m->tab.ensure((size_t)NT * std::max(W, 2) * sizeof(double)))) return rc;
+  if ((rc = m->work0.ensure(consts.size() * sizeof(double)))) return rc;
+  if ((rc = m->work1.ensure(blob.size()))) return rc;
+  // Gathers are unconditional (invalid columns carry a zero coefficient): the buffers are zero-filled once per solve, row
+  // padding included, with slack in front of the first and behind the last matrix.
+  const size_t slack = 64;  // elements
+  const size_t w2_bytes = (4 * (size_t)B * n_pad + 2 * slack) * 16;
+  if ((rc = m->work2.ensure(w2_bytes))) return rc;
+  CASQ_CUDA(cudaMemsetAsync(m->work2.p, 0, w2_bytes, st));
+  if ((rc = m->work3.ensure(3 * (size_t)B * cp.NC * 16))) return rc;
+  CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, g.times.data(), NT * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->work0.p, consts.data(), consts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CASQ_CUDA(cudaMemcpyAsync(m->work1.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+  {
+    const long long nthreads = NT * (KA + NF);
+    sv_general_table_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(
+        (const double*)m->tab_times.p, NT, KA, NF, W, (const double*)m->work0.p, (const double*)m->work0.p + KA,
+        (double*)m->tab.p);
+    CASQ_CUDA(cudaGetLastError());
+  }
+  unsigned char* dev = (unsigned char*)m->work1.p;
+  LbArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.ld = ld; a.KA = KA; a.NF = NF; a.NTF = NTF; a.W = W;
+  a.tf_sig = (const int*)(dev + o_tfsig);
+  a.tf_freq = (const int*)(dev + o_tffreq);
+  a.table = (const double*)m->tab.p;
+  a.idx = (const int*)m->tab_idx.p;
+  a.params = params_dev;
+  a.Bp = B;
+  a.slots = ds;
+  LcArgs c;
+  memset(&c, 0, sizeof(c));
+  c.d = d; c.ld = ld; c.nq = cp.nq; c.ntile = ntile; c.npairs = npairs; c.NC = cp.NC; c.NS = cp.NS;
+  c.n2 = cp.n2; c.u_base = cp.u_base; c.w_base = cp.w_base;
+  for (int k = 0; k < cp.n2; k++) {
+    c.two_q[k] = cp.two_q[k];
+    c.two_dir[k] = cp.two_dir[k];
+  }
+  c.drv_mask = cp.drv_mask;
+  c.pair_ij = (const int*)(dev + o_pij);
+  c.G = (const double2*)(dev + o_G);
+  c.slot_start = (const int*)(dev + o_ss);
+  c.atom_val = (const double2*)(dev + o_av);
+  c.atom_code = (const int*)(dev + o_ac);
+  const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
+  const size_t smem_stage = lindblad_chain_smem(cp.NC);
+  const bool low_only = (cp.drv_mask & 6u) == 0;  // only site 0 of the low three is driven (cfg 4): leaner in-tile code
+  CASQ_CUDA(cudaFuncSetAttribute(lindblad_chain_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
+  void (*stage_fn)(const LcArgs, int, const LbStage) = nullptr;
+#define LC_PICK(NQ_)                                                                                   \
+  if (cp.nq == NQ_) stage_fn = low_only ? lindblad_chain_stage_kernel<NQ_, 1> : lindblad_chain_stage_kernel<NQ_, 7>;
+  LC_PICK(3) LC_PICK(4) LC_PICK(5) LC_PICK(6)
+#undef LC_PICK
+  if (!stage_fn) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "chain kernel: %d sites", cp.nq);
+  CASQ_CUDA(cudaFuncSetAttribute(stage_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
+
+  struct Part {
+    LbArgs a;
+    LcArgs c;
+    double2* bufs[4];
+    long long b0, Bc;
+    cudaStream_t st;
+  };
+  int n_parts = (int)std::min<long long>(4, std::max<long long>(1, B / 4));
+  if (const char* e = getenv("CASQ_LB_PARTS")) n_parts = std::min(4, std::max(1, atoi(e)));
+  n_parts = (int)std::min<long long>(n_parts, B);
+  if (n_parts > 1 && !m->ev_fork) CASQ_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i + 1 < n_parts; i++)
+    if (!m->aux_stream[i]) {
+      CASQ_CUDA(cudaStreamCreateWithFlags(&m->aux_stream[i], cudaStreamNonBlocking));
+      CASQ_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+    }
+  Part parts[4];
+  for (int pi = 0; pi < n_parts; pi++) {
+    Part& P = parts[pi];
+    P.b0 = (long long)B * pi / n_parts;
+    P.Bc = (long long)B * (pi + 1) / n_parts - P.b0;
+    P.st = pi == 0 ? st : m->aux_stream[pi - 1];
+    P.a = a;
+    P.a.B = P.Bc;
+    P.a.b0 = P.b0;
+    P.c = c;
+    P.c.B = P.Bc;
+    P.c.ctab = (double2*)m->work3.p + 3 * (size_t)P.b0 * cp.NC;
+    for (int i = 0; i < 4; i++) P.bufs[i] = (double2*)m->work2.p + slack + (size_t)i * B * n_pad + (size_t)P.b0 * n_pad;
+  }
+  if (n_parts > 1) {
+    CASQ_CUDA(cudaEventRecord(m->ev_fork, st));
+    for (int i = 0; i + 1 < n_parts; i++) CASQ_CUDA(cudaStreamWaitEvent(m->aux_stream[i], m->ev_fork, 0));
+  }
+  for (int pi = 0; pi < n_parts; pi++) {
+    Part& P = parts[pi];
+    const long long n = P.Bc * (long long)n_per;
+    const double2* r0p = (const double2*)rho0_dev + (rho0_batched ? (size_t)P.b0 * n_per : 0);
+    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, r0p, rho0_batched, P.bufs[0]);
+    CASQ_CUDA(cudaGetLastError());
+  }
+  int t_slot = 0;
+  auto emit = [&]() -> int {
+    for (int pi = 0; pi < n_parts; pi++) {
+      Part& P = parts[pi];
+      if (out_rho_dev) {
+        const long long n = P.Bc * (long long)n_per;
+        lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, P.bufs[0],
+                                                                              (double2*)out_rho_dev + (size_t)P.b0 * T * n_per, T, t_slot);
+        CASQ_CUDA(cudaGetLastError());
+      }
+      if (out_pops_dev) {
+        lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)P.Bc), 256, 0, P.st>>>(d, ld, P.bufs[0], (const double2*)(dev + o_V),
+                                                                                (const double2*)(dev + o_ph) + (size_t)t_slot * d,
+                                                                                out_pops_dev + (size_t)P.b0 * T * d, T, t_slot);
+        CASQ_CUDA(cudaGetLastError());
+      }
+    }
+    t_slot++;
+    return CASQ_OK;
+  };
+  if (g.out_keep[0] && (rc = emit())) return rc;
+  long long pos = 0;
+  for (size_t p = 0; p < g.piece_nsteps.size(); p++) {
+    const int n = g.piece_nsteps[p];
+    const double h_piece = g.piece_h[p];
+    for (int s = 0; s < n; s++) {
+      for (int pi = 0; pi < n_parts; pi++) {
+        Part& P = parts[pi];
+        const long long tasks = P.Bc * (long long)npairs;
+        const unsigned grid = (unsigned)((tasks + LC_WARPS - 1) / LC_WARPS);
+        lindblad_chain_coef_kernel<<<dim3((unsigned)P.Bc, 3), 128, smem_coef, P.st>>>(P.a, P.c, pos);
+        for (int stage = 1; stage <= 4; stage++) {
+          const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);
+          LbStage sg;
+          sg.in = P.bufs[stage - 1];
+          sg.y = P.bufs[0];
+          sg.y1 = P.bufs[1];
+          sg.y2 = P.bufs[2];
+          sg.out = stage == 4 ? P.bufs[0] : P.bufs[stage];
+          sg.stage = stage;
+          sg.h = h_piece;
+          stage_fn<<<grid, 32 * LC_WARPS, smem_stage, P.st>>>(P.c, set, sg);
+        }
+      }
+      pos += 2;
+    }
+    CASQ_CUDA(cudaGetLastError());
+    pos += 1;
+    if (g.out_keep[p + 1] && (rc = emit())) return rc;
+  }
+  for (int i = 0; i + 1 < n_parts; i++) {
+    CASQ_CUDA(cudaEventRecord(m->ev_join[i], m->aux_stream[i]));
+    CASQ_CUDA(cudaStreamWaitEvent(st, m->ev_join[i], 0));
+  }
+  return CASQ_OK;
+}
 }  // namespace
 
 extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pulse_slot* slots, int64_t B,
@@ -154,6 +563,15 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   for (int i = 0; i < d; i++)
     for (int j = 0; j < d; j++)
       if (std::abs(D[i * d + j]) != 0.0) one.push_back({i, j, 0, -0.5 * D[i * d + j], bohr(i, j)});
+  if (B > 65535) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_lindblad_rk4: at most 65535 density matrices per call");
+  {
+    // chains of three-level sites (every casq TransmonModel with >= 3 qubits) take the register-tiled kernel
+    Builder probe = bld;
+    const ChainPlan cp = lc_analyze(m, probe, one, (d + 7) & ~7);
+    if (cp.ok)
+      return lindblad_run_chain(m, cp, probe, KA, active, ds, n_total, B, params_dev, rho0_dev, rho0_batched, t0, t1, max_dt, T,
+                                t_eval, out_rho_dev, out_pops_dev, st);
+  }
   ClassTab os;
   bld.place(one, &os);
   if (os.delta.empty()) {  // completely free evolution: keep one empty class so the kernel has something to index
