@@ -471,7 +471,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
       for (int pi = 0; pi < n_parts; pi++) {
         Part& P = parts[pi];
         const long long tasks = P.Bc * (long long)npairs;
-        const unsigned grid = (unsigned)((tasks + LC_WARPS - 1) / LC_WARPS);
+        const unsigned grid = (unsigned)tasks;  // one block of three warps per tile pair
         lindblad_chain_coef_kernel<<<dim3((unsigned)P.Bc, 3), 128, smem_coef, P.st>>>(P.a, P.c, pos);
         for (int stage = 1; stage <= 4; stage++) {
           const int set = stage == 1 ? 0 : (stage == 4 ? 2 : 1);

@@ -5,14 +5,15 @@
 // operators handed over the C ABI (every element must fit; anything else runs the generic shift-class kernel of
 // lindblad_stage.cuh) and this kernel exploits it:
 //
-//   index r = sum_q x_q 3^q.   One WARP owns the 27 x 27 tile pair (I,J), (J,I), I <= J, of one trajectory; lane = column
-//   inside the tile, and a lane keeps the 27 accumulators of its column (the digits x_0, x_1, x_2 of the row index) in
-//   REGISTERS.  Every operator that acts inside the low three sites (X_0..X_2, J_01, J_12: 4.1 of the 5.9 non-zeros per row
-//   of A = -iH_F - D_F/2 for ibmq_manila) is then applied from ONE load of each source element: a loaded element feeds
-//   ~4 complex FMAs instead of one (the generic kernel gathers once per non-zero: ~100 L1 wavefronts per 32 outputs, the
-//   bound ncu showed in profiles/r01_ncu_lindblad_fused_stage.txt).  Operators reaching outside the tile (J_23, J_34, X_3..,
-//   and the two-sided terms L rho L^+) are "gather terms": one extra row load each, with warp-uniform or per-lane
-//   coefficients; all address offsets are immediates.
+//   index r = sum_q x_q 3^q.   One BLOCK of three warps owns the 27 x 27 tile pair (I,J), (J,I), I <= J, of one trajectory;
+//   warp g owns the nine rows with x_2 = g, lane = column inside the tile, and a lane keeps the 9 accumulators of its
+//   column (digits x_0, x_1 of the row index) in REGISTERS.  The operators that act inside the low two sites (X_0, X_1,
+//   J_01) are applied from ONE load of each source element; everything else is a "gather term" with a warp-uniform
+//   coefficient (x_2 and the tile digits are warp-uniform: X_2.., J_23, J_34..) or a short straight-line block (J_12, the
+//   two-sided terms L rho L^+ of sites 0..2 with per-lane coefficients).  Against the generic kernel: no per-row lists, no
+//   address arithmetic (all offsets are immediates), ~35 % fewer gathered rows, and ~20 resident warps per SM with nine
+//   independent loads in flight each (a first version with 27 accumulators per lane needed 252 registers: 8 warps per
+//   SM, 57 % of its stall samples on the load scoreboard, 212 traj/s).
 //   k = M + M^+ + sum_j L_j rho L_j^+ with M = A rho is formed as in the generic kernel: M_JI is computed with left gathers,
 //   transposed through a per-warp shared tile, the RK4 combination is fused, and the mirror tile out[J,I] = out[I,J]^+ is
 //   written from the shared tile, so every stage output is exactly Hermitian and y[J,I], y1[J,I].. are never read.
@@ -22,7 +23,7 @@
 #include "lindblad_stage.cuh"
 
 #define LC_T 27          // tile edge = 3 sites
-#define LC_WARPS 8       // warps (tile pairs) per block
+#define LC_WARPS 3       // warps per block = per tile pair: warp g owns the rows with x_2 = g
 #define LC_MAXQ 6        // sites
 #define LC_MAX2 8        // two-sided single-site terms
 #define LC_MAXTERMS 32   // gather terms per task
@@ -98,117 +99,120 @@ __global__ void __launch_bounds__(128) lindblad_chain_coef_kernel(const LbArgs a
 
 __host__ __device__ constexpr int lc_pow3(int q) { return q == 0 ? 1 : 3 * lc_pow3(q - 1); }
 
-// The in-tile part of M = A rho for the 27 rows of a row tile at this lane's column: every source row is loaded once and
-// applied to all the accumulators it feeds (X_0..X_2 ladder elements, J_01 and J_12 exchange elements).  ct = the warp's
-// coefficient table in shared memory (broadcast reads).  XLOW: bit q set = the ladder slots of site q are compiled in.
-template <int NQ, int LD, int XLOW>
-__device__ __forceinline__ void lc_in_tile(double2 (&acc)[LC_T], const double2* __restrict__ p, const double2* ct) {
-  const double2* cJ = ct + 4 * NQ;
+__device__ __forceinline__ void lc_zero9(double2 (&acc)[9]) {
 #pragma unroll
-  for (int s = 0; s < LC_T; s++) {  // source row s of the tile
-    const double2 v = __ldg(p + s * LD);
-    const int xs[3] = {s % 3, (s / 3) % 3, s / 9};
-    const int pw[3] = {1, 3, 9};
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      if (!((XLOW >> q) & 1)) continue;
-      // A[t, s] with s = t + 3^q: slot X(q, 0, n = x_q(t) = x_q(s) - 1)
-      if (xs[q] >= 1) lc_cfma(acc[s - pw[q]], ct[(q * 2 + 0) * 2 + xs[q] - 1], v);
-      // A[t, s] with s = t - 3^q: slot X(q, 1, n = x_q(t) - 1 = x_q(s))
-      if (xs[q] <= 1) lc_cfma(acc[s + pw[q]], ct[(q * 2 + 1) * 2 + xs[q]], v);
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      const int sh = pw[q + 1] - pw[q];
-      // dir 0: s = t + sh; n = x_q(t) - 1 = x_q(s), m = x_{q+1}(t) = x_{q+1}(s) - 1
-      if (xs[q] <= 1 && xs[q + 1] >= 1) lc_cfma(acc[s - sh], cJ[((q * 2 + 0) * 2 + xs[q]) * 2 + xs[q + 1] - 1], v);
-      // dir 1: s = t - sh; n = x_q(t) = x_q(s) - 1, m = x_{q+1}(t) - 1 = x_{q+1}(s)
-      if (xs[q] >= 1 && xs[q + 1] <= 1) lc_cfma(acc[s + sh], cJ[((q * 2 + 1) * 2 + xs[q] - 1) * 2 + xs[q + 1]], v);
-    }
-  }
+  for (int t = 0; t < 9; t++) acc[t] = make_double2(0.0, 0.0);
 }
 
-// Gather terms.  Every load is unconditional (lanes 27..31 alias lane 26; per-lane invalid columns carry a zero
-// coefficient and read initialised memory: the buffers are zero-filled with slack on both sides).
-//   * "all rows" terms (operators whose source lies in another row tile with the same in-tile row: X_q, J_q,q+1 and the
-//     two-sided terms of sites q >= 3): a run-time list per task, one warp-uniform coefficient each;
-//   * terms that depend on an in-tile digit (J_23, the two-sided terms of sites 0..2): straight-line blocks below.
+// nine rows of one group from another place (same local rows), one coefficient
 template <int LD>
-__device__ __forceinline__ void lc_apply_all(double2 (&acc)[LC_T], const double2* __restrict__ src, const double2 c0) {
+__device__ __forceinline__ void lc_apply9(double2 (&acc)[9], const double2* __restrict__ src, const double2 c) {
+  double2 v[9];
 #pragma unroll
-  for (int t = 0; t < LC_T; t++) lc_cfma(acc[t], c0, __ldg(src + t * LD));
+  for (int t = 0; t < 9; t++) v[t] = __ldg(src + t * LD);
+#pragma unroll
+  for (int t = 0; t < 9; t++) lc_cfma(acc[t], c, v[t]);
 }
-// rows whose digit Q is LO take c0, rows whose digit Q is LO + 1 take c1
+
+// rows of the group whose digit Q (0 or 1) is LO take c0, those whose digit is LO + 1 take c1 (six loads)
 template <int LD, int Q, int LO>
-__device__ __forceinline__ void lc_apply_digit(double2 (&acc)[LC_T], const double2* __restrict__ src, const double2 c0, const double2 c1) {
+__device__ __forceinline__ void lc_apply_digit9(double2 (&acc)[9], const double2* __restrict__ src, const double2 c0, const double2 c1) {
+  double2 v[9];
 #pragma unroll
-  for (int t = 0; t < LC_T; t++) {
-    constexpr int P3 = Q == 0 ? 1 : (Q == 1 ? 3 : 9);
-    const int x = (t / P3) % 3;
-    if (x == LO) lc_cfma(acc[t], c0, __ldg(src + t * LD));
-    if (x == LO + 1) lc_cfma(acc[t], c1, __ldg(src + t * LD));
+  for (int t = 0; t < 9; t++) {
+    const int x = Q == 0 ? t % 3 : t / 3;
+    if (x == LO || x == LO + 1) v[t] = __ldg(src + t * LD);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const int x = Q == 0 ? t % 3 : t / 3;
+    if (x == LO) lc_cfma(acc[t], c0, v[t]);
+    if (x == LO + 1) lc_cfma(acc[t], c1, v[t]);
   }
 }
 
-struct LcTask {  // per-warp task description in shared memory (written by lane 0)
-  int n_all[3];        // end of the all-rows term list of seg 0, 1, 2 (lists are stored back to back)
-  int j23[2][2];       // [row tile: 0 = J (seg 0), 1 = I (seg 1)][dir]: J_23 term present
-  int j23_slot[2][2];  // slot of the x_2 = LO coefficient (the LO + 1 one is 2 slots further)
-  int off[LC_MAXTERMS];
-  int slot[LC_MAXTERMS];
+// The part of M = A rho that stays inside the nine rows (x_0, x_1) of a group: X_0, X_1 ladder and J_01 exchange elements,
+// every source row loaded once.  XLOW bit q = the ladder slots of site q are compiled in.
+template <int NQ, int LD, int XLOW>
+__device__ __forceinline__ void lc_in_group(double2 (&acc)[9], const double2* __restrict__ p, const double2* ct) {
+  const double2* cJ = ct + 4 * NQ;
+  double2 v[9];
+#pragma unroll
+  for (int s = 0; s < 9; s++) v[s] = __ldg(p + s * LD);
+#pragma unroll
+  for (int s = 0; s < 9; s++) {
+    const int x0 = s % 3, x1 = s / 3;
+    if (XLOW & 1) {
+      if (x0 >= 1) lc_cfma(acc[s - 1], ct[(0 * 2 + 0) * 2 + x0 - 1], v[s]);  // A[t, s = t + 1]: X(0, 0, n = x_0(t))
+      if (x0 <= 1) lc_cfma(acc[s + 1], ct[(0 * 2 + 1) * 2 + x0], v[s]);      // A[t, s = t - 1]: X(0, 1, n = x_0(t) - 1)
+    }
+    if (XLOW & 2) {
+      if (x1 >= 1) lc_cfma(acc[s - 3], ct[(1 * 2 + 0) * 2 + x1 - 1], v[s]);
+      if (x1 <= 1) lc_cfma(acc[s + 3], ct[(1 * 2 + 1) * 2 + x1], v[s]);
+    }
+    // J_01, s = t + 2: n = x_0(t) - 1 = x_0(s), m = x_1(t) = x_1(s) - 1;  s = t - 2: n = x_0(t) = x_0(s) - 1, m = x_1(t) - 1 = x_1(s)
+    if (x0 <= 1 && x1 >= 1) lc_cfma(acc[s - 2], cJ[((0 * 2 + 0) * 2 + x0) * 2 + x1 - 1], v[s]);
+    if (x0 >= 1 && x1 <= 1) lc_cfma(acc[s + 2], cJ[((0 * 2 + 1) * 2 + x0 - 1) * 2 + x1], v[s]);
+  }
+}
+
+struct LcList {  // gather terms of one warp for one segment: nine rows each, warp-uniform coefficient
+  int n;
+  int off[15];
+  int slot[15];
+  int pad;
 };
 
+// one-sided gather terms of the rows (R, x_2 = g): everything of A that leaves the nine-row group except J_12
 template <int NQ, int LD>
-__device__ __forceinline__ void lc_build_one_sided(LcTask* tk, int which, int& n, int R, unsigned drv_mask) {
+__device__ __forceinline__ void lc_build_one_sided(LcList* L, int R, int g, unsigned drv_mask) {
   const int jbase = 4 * NQ;
+  int n = 0;
   int xd[LC_MAXQ + 1];
   int rr = R;
   for (int q = 3; q <= LC_MAXQ; q++) {  // tile digits: x_3 = R % 3, x_4 = (R / 3) % 3, ...
     xd[q] = rr % 3;
     rr /= 3;
   }
-  tk->j23[which][0] = tk->j23[which][1] = 0;
-  if (NQ >= 4) {  // J_23: digit 2 lives inside the tile, digit 3 in the tile index
+  if ((drv_mask >> 2) & 1u) {  // X_2: source group g + 1 / g - 1 of the same tile
+    if (g <= 1) { L->off[n] = 9 * LD; L->slot[n++] = (2 * 2 + 0) * 2 + g; }
+    if (g >= 1) { L->off[n] = -9 * LD; L->slot[n++] = (2 * 2 + 1) * 2 + g - 1; }
+  }
+  if (NQ >= 4) {  // J_23: r + 27 - 9 (x_2 >= 1, x_3 <= 1: n = x_2 - 1, m = x_3) and r - 27 + 9 (x_2 <= 1, x_3 >= 1: n = x_2, m = x_3 - 1)
     const int x3 = xd[3];
-    // dir 0: source r + 27 - 9, rows with x_2(t) = 1, 2: n = x_2(t) - 1, m = x_3.  slot(n, m) = jbase + ((2*2+0)*2 + n)*2 + m
-    tk->j23[which][0] = x3 <= 1;
-    tk->j23_slot[which][0] = jbase + ((2 * 2 + 0) * 2 + 0) * 2 + x3;
-    // dir 1: source r - 27 + 9, rows with x_2(t) = 0, 1: n = x_2(t), m = x_3 - 1
-    tk->j23[which][1] = x3 >= 1;
-    tk->j23_slot[which][1] = jbase + ((2 * 2 + 1) * 2 + 0) * 2 + x3 - 1;
+    if (g >= 1 && x3 <= 1) { L->off[n] = 18 * LD; L->slot[n++] = jbase + ((2 * 2 + 0) * 2 + g - 1) * 2 + x3; }
+    if (g <= 1 && x3 >= 1) { L->off[n] = -18 * LD; L->slot[n++] = jbase + ((2 * 2 + 1) * 2 + g) * 2 + x3 - 1; }
   }
   int pw = 27;
   for (int q = 3; q < NQ; q++, pw *= 3) {
     const int xq = xd[q];
     if ((drv_mask >> q) & 1u) {
-      if (xq <= 1) { tk->off[n] = pw * LD; tk->slot[n++] = (q * 2 + 0) * 2 + xq; }
-      if (xq >= 1) { tk->off[n] = -pw * LD; tk->slot[n++] = (q * 2 + 1) * 2 + xq - 1; }
+      if (xq <= 1) { L->off[n] = pw * LD; L->slot[n++] = (q * 2 + 0) * 2 + xq; }
+      if (xq >= 1) { L->off[n] = -pw * LD; L->slot[n++] = (q * 2 + 1) * 2 + xq - 1; }
     }
     if (q + 1 < NQ) {
       const int xq1 = xd[q + 1];
-      if (xq >= 1 && xq1 <= 1) { tk->off[n] = 2 * pw * LD; tk->slot[n++] = jbase + ((q * 2 + 0) * 2 + xq - 1) * 2 + xq1; }
-      if (xq <= 1 && xq1 >= 1) { tk->off[n] = -2 * pw * LD; tk->slot[n++] = jbase + ((q * 2 + 1) * 2 + xq) * 2 + xq1 - 1; }
+      if (xq >= 1 && xq1 <= 1) { L->off[n] = 2 * pw * LD; L->slot[n++] = jbase + ((q * 2 + 0) * 2 + xq - 1) * 2 + xq1; }
+      if (xq <= 1 && xq1 >= 1) { L->off[n] = -2 * pw * LD; L->slot[n++] = jbase + ((q * 2 + 1) * 2 + xq) * 2 + xq1 - 1; }
     }
   }
+  L->n = n;
 }
 
 static inline size_t lindblad_chain_smem(int NC) {
-  return (size_t)LC_WARPS * ((size_t)LC_T * LC_T * 16 + (size_t)((NC + 1) & ~1) * 16 + ((sizeof(LcTask) + 15) & ~(size_t)15));
+  return (size_t)LC_T * LC_T * 16 + (size_t)((NC + 1) & ~1) * 16 + 3 * LC_WARPS * sizeof(LcList);
 }
 
 template <int NQ, int XLOW>
-__global__ void __launch_bounds__(32 * LC_WARPS, 1) lindblad_chain_stage_kernel(const LcArgs a, int set, const LbStage s) {
+__global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(const LcArgs a, int set, const LbStage s) {
   constexpr int D = lc_pow3(NQ), LD = (D + 7) & ~7;
   extern __shared__ __align__(16) unsigned char lc_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int NCs = (a.NC + 1) & ~1;
-  const size_t per_warp = (size_t)LC_T * LC_T * 16 + (size_t)NCs * 16 + ((sizeof(LcTask) + 15) & ~(size_t)15);
-  unsigned char* mine = lc_smem + (size_t)warp * per_warp;
-  double2* sT = reinterpret_cast<double2*>(mine);              // [27][27]
+  double2* sT = reinterpret_cast<double2*>(lc_smem);           // [27][27]
   double2* ct = sT + LC_T * LC_T;                              // [NC]
-  LcTask* tk = reinterpret_cast<LcTask*>(ct + NCs);
-  const long long task = (long long)blockIdx.x * LC_WARPS + warp;
-  if (task >= a.B * a.npairs) return;
+  LcList* lists = reinterpret_cast<LcList*>(ct + NCs) + 3 * g; // [warp][seg]
+  const long long task = blockIdx.x;
   const long long b = task / a.npairs;
   const int pr = (int)(task - b * a.npairs);
   const int I = a.pair_ij[2 * pr], J = a.pair_ij[2 * pr + 1];
@@ -217,14 +221,12 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 1) lindblad_chain_stage_kernel(
   const int cl = active ? lane : LC_T - 1;  // lanes 27..31 shadow lane 26 (loads stay in bounds, nothing is stored)
   {
     const double2* src = a.ctab + ((long long)set * a.B + b) * a.NC;
-    for (int i = lane; i < a.NC; i += 32) ct[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < a.NC; i += 32 * LC_WARPS) ct[i] = __ldg(src + i);
   }
   if (lane == 0) {
+    if (!diag) lc_build_one_sided<NQ, LD>(lists + 0, J, g, a.drv_mask);
+    lc_build_one_sided<NQ, LD>(lists + 1, I, g, a.drv_mask);
     int n = 0;
-    if (!diag) lc_build_one_sided<NQ, LD>(tk, 0, n, J, a.drv_mask);
-    tk->n_all[0] = n;
-    lc_build_one_sided<NQ, LD>(tk, 1, n, I, a.drv_mask);
-    tk->n_all[1] = n;
     for (int k = 0; k < a.n2; k++) {  // two-sided terms of the sites in the tile INDEX: warp-uniform coefficient W(k, nr, nc)
       const int q = a.two_q[k];
       if (q <= 2) continue;
@@ -236,87 +238,89 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 1) lindblad_chain_stage_kernel(
       }
       const int nr = ti % 3, nc = tj % 3;
       if (nr > 1 || nc > 1) continue;
-      tk->off[n] = pw * 27 * (LD + 1);
-      tk->slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
+      lists[2].off[n] = pw * 27 * (LD + 1);
+      lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
     }
-    tk->n_all[2] = n;
+    lists[2].n = n;
   }
-  __syncwarp();
+  __syncthreads();
   const long long base = b * (long long)D * LD;
   const double2* in = s.in + base;
-  const long long o0 = (long long)(LC_T * I) * LD + LC_T * J + cl;
-  const int x0l = cl % 3, x1l = (cl / 3) % 3, x2l = cl / 9;
-  double2 acc[LC_T];
+  const long long o0 = (long long)(LC_T * I + 9 * g) * LD + LC_T * J + cl;   // this warp's rows of tile (I, J)
+  const double2* cJ12 = ct + 4 * NQ + (1 * 2 + 0) * 4;  // J(1, dir, n, m) = cJ12[(dir*2 + n)*2 + m]
+  double2 acc[9];
   // seg 0: M_JI = (A rho)[J, I] -> sT;  seg 1: M_IJ (diagonal pair: also -> sT);  seg 2: + two-sided terms of (I, J)
 #pragma unroll 1
   for (int seg = diag ? 1 : 0; seg < 3; seg++) {
-    const double2* p = seg == 0 ? in + (long long)(LC_T * J) * LD + LC_T * I + cl : in + o0;
+    const double2* p = seg == 0 ? in + (long long)(LC_T * J + 9 * g) * LD + LC_T * I + cl : in + o0;
     if (seg < 2) {
-#pragma unroll
-      for (int t = 0; t < LC_T; t++) acc[t] = make_double2(0.0, 0.0);
-      lc_in_tile<NQ, LD, XLOW>(acc, p, ct);
-      if (NQ >= 4) {
-        if (tk->j23[seg][0]) {
-          const int sl = tk->j23_slot[seg][0];
-          lc_apply_digit<LD, 2, 1>(acc, p + 18 * LD, ct[sl], ct[sl + 2]);
-        }
-        if (tk->j23[seg][1]) {
-          const int sl = tk->j23_slot[seg][1];
-          lc_apply_digit<LD, 2, 0>(acc, p - 18 * LD, ct[sl], ct[sl + 2]);
-        }
-      }
+      lc_zero9(acc);
+      lc_in_group<NQ, LD, XLOW>(acc, p, ct);
+      // J_12 inside the tile: s = t + 6 (x_1(t) >= 1, g <= 1: n = x_1(t) - 1, m = g);  s = t - 6 (x_1(t) <= 1, g >= 1: n = x_1(t), m = g - 1)
+      if (g <= 1) lc_apply_digit9<LD, 1, 1>(acc, p + 6 * LD, cJ12[(0 * 2 + 0) * 2 + g], cJ12[(0 * 2 + 1) * 2 + g]);
+      if (g >= 1) lc_apply_digit9<LD, 1, 0>(acc, p - 6 * LD, cJ12[(1 * 2 + 0) * 2 + g - 1], cJ12[(1 * 2 + 1) * 2 + g - 1]);
     } else {
-      // two-sided terms of the sites inside the tile (lowering operators): rho[r + 3^q, c + 3^q], rows and lanes with digit
-      // q <= 1; coefficient W(k, nr = x_q(row), nc = x_q(lane))
+      // two-sided terms of the sites inside the tile (lowering operators): rho[r + 3^q, c + 3^q] for rows and lanes whose
+      // digit q is <= 1; coefficient W(k, nr = x_q(row), nc = x_q(lane)) = ct[w_base + 4k + 2 nr + nc]
       const double2 z = make_double2(0.0, 0.0);
       for (int k = 0; k < a.n2; k++) {
         const int q = a.two_q[k];
         if (q > 2) continue;
         const int wb = a.w_base + k * 4;
-        const int xl = q == 0 ? x0l : (q == 1 ? x1l : x2l);
+        const int xl = q == 0 ? cl % 3 : (q == 1 ? (cl / 3) % 3 : cl / 9);
         const bool ok = xl <= 1;
-        const double2 c0 = ok ? ct[wb + xl] : z, c1 = ok ? ct[wb + 2 + xl] : z;
-        if (q == 0) lc_apply_digit<LD, 0, 0>(acc, p + (LD + 1), c0, c1);
-        if (q == 1) lc_apply_digit<LD, 1, 0>(acc, p + 3 * (LD + 1), c0, c1);
-        if (q == 2) lc_apply_digit<LD, 2, 0>(acc, p + 9 * (LD + 1), c0, c1);
+        const int xx = ok ? xl : 0;
+        if (q == 0) lc_apply_digit9<LD, 0, 0>(acc, p + (LD + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 1) lc_apply_digit9<LD, 1, 0>(acc, p + 3 * (LD + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 2 && g <= 1) lc_apply9<LD>(acc, p + 9 * (LD + 1), ok ? ct[wb + 2 * g + xx] : z);
       }
     }
     {
-      const int first = seg == 0 ? 0 : tk->n_all[seg - 1], last = tk->n_all[seg];
+      const LcList* L = lists + seg;
+      const int n = L->n;
 #pragma unroll 1
-      for (int i = first; i < last; i++) lc_apply_all<LD>(acc, p + tk->off[i], ct[tk->slot[i]]);
+      for (int i = 0; i < n; i++) lc_apply9<LD>(acc, p + L->off[i], ct[L->slot[i]]);
     }
     if ((seg == 0 || (seg == 1 && diag)) && active) {
 #pragma unroll
-      for (int t = 0; t < LC_T; t++) sT[t * LC_T + lane] = acc[t];
+      for (int t = 0; t < 9; t++) sT[(9 * g + t) * LC_T + lane] = acc[t];
     }
   }
-  __syncwarp();
+  __syncthreads();
   // ---- epilogue: k = M_IJ + M_JI^+ + G o rho, RK4 combination, store; the result replaces the consumed sT slot
   if (active) {
     const double2* p = in + o0;
-    const double2* g = a.G + o0;
+    const double2* gp = a.G + o0;
 #pragma unroll
-    for (int t = 0; t < LC_T; t++) {
-      const long long o = base + o0 + (long long)t * LD;
-      const double2 y0 = s.y[o];
-      const double2 v = __ldg(p + t * LD), gg = __ldg(g + t * LD);
-      const double2 m = sT[lane * LC_T + t];  // M_JI(J*27 + lane, I*27 + t)
-      double2 k = make_double2(acc[t].x + m.x, acc[t].y - m.y);
-      lc_cfma(k, gg, v);
-      const double2 res = lb_rk4_combine(s, o, y0, k.x, k.y);
-      s.out[o] = res;
-      if (!diag) sT[lane * LC_T + t] = res;
+    for (int t0 = 0; t0 < 9; t0 += 3) {  // three rows at a time: nine independent loads in flight, 36 registers
+      double2 y0[3], v[3], gg[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        y0[u] = s.y[base + o0 + (long long)(t0 + u) * LD];
+        v[u] = __ldg(p + (t0 + u) * LD);
+        gg[u] = __ldg(gp + (t0 + u) * LD);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int t = t0 + u;
+        const long long o = base + o0 + (long long)t * LD;
+        const double2 m = sT[lane * LC_T + 9 * g + t];  // M_JI(J*27 + lane, I*27 + 9g + t)
+        double2 k = make_double2(acc[t].x + m.x, acc[t].y - m.y);
+        lc_cfma(k, gg[u], v[u]);
+        const double2 res = lb_rk4_combine(s, o, y0[u], k.x, k.y);
+        s.out[o] = res;
+        if (!diag) sT[lane * LC_T + 9 * g + t] = res;
+      }
     }
   }
   if (diag) return;
-  __syncwarp();
-  // ---- mirror tile: out(J*27 + t, I*27 + lane) = conj(out(I*27 + lane, J*27 + t)) = conj(sT[t][lane])
+  __syncthreads();
+  // ---- mirror tile: out(J*27 + r, I*27 + lane) = conj(out(I*27 + lane, J*27 + r)) = conj(sT[r][lane]), r = 9g + t
   if (active) {
-    const long long om = base + (long long)(LC_T * J) * LD + LC_T * I + lane;
+    const long long om = base + (long long)(LC_T * J + 9 * g) * LD + LC_T * I + lane;
 #pragma unroll
-    for (int t = 0; t < LC_T; t++) {
-      const double2 r = sT[t * LC_T + lane];
+    for (int t = 0; t < 9; t++) {
+      const double2 r = sT[(9 * g + t) * LC_T + lane];
       s.out[om + (long long)t * LD] = make_double2(r.x, -r.y);
     }
   }
