@@ -10,7 +10,10 @@ import numpy as np
 
 from .common.exceptions import CasqError
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcasq_b200.so"
+import os
+
+# CASQ_B200_LIB: tuning knob -- load another build of the same library (kernel variants compared in one GPU session)
+_LIB_PATH = Path(os.environ.get("CASQ_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libcasq_b200.so")
 _lib = None
 
 NPARAM = 5

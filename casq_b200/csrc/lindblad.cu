@@ -165,7 +165,7 @@ static bool lc_consistent(const SlotRows& sr, double tol, std::map<int, cplx>* r
   return true;
 }
 
-static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector<Atom>& one, int ld) {
+static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector<Atom>& one) {
   ChainPlan P;
   const int d = m->d;
   int nq = 0, dd = 1;
@@ -178,10 +178,8 @@ static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector
   P.nq = nq;
   const int NX = 4 * nq, NJ = 8 * (nq - 1);
   std::vector<SlotRows> slots(NX + NJ);
-  long long pw = 1;
   for (int s = 0; s < NX; s++) slots[s].expected = d / 3;
   for (int s = 0; s < NJ; s++) slots[NX + s].expected = d / 9;
-  (void)pw;
   std::vector<cplx> adiag(d, cplx(0.0));
   for (const Atom& at : one) {
     const int code = bld.tf_id(at.sig, at.omega);
@@ -265,12 +263,13 @@ static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector
   for (int s = 0; s < NX + NJ; s++) put(reps[s]);
   for (const auto& r : ureps) put(r);
   // G[r,c] = A_rr + conj(A_cc) + sum over diagonal L_j of l_j(r) conj(l_j(c))
+  const int ld = (d / LC_T) * LC_TS;  // the chain path's padded-tile storage (lb_col)
   P.G.assign((size_t)d * ld, cplx(0.0));
   for (int r = 0; r < d; r++)
     for (int c = 0; c < d; c++) {
       cplx g = adiag[r] + std::conj(adiag[c]);
       for (const auto& l : diagL) g += l[r] * std::conj(l[c]);
-      P.G[(size_t)r * ld + c] = g;
+      P.G[(size_t)r * ld + c + (c / LC_T) * (LC_TS - LC_T)] = g;
     }
   P.ok = true;
   return P;
@@ -282,7 +281,8 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
                               int n_total, int64_t B, const double* params_dev, const double* rho0_dev, int rho0_batched,
                               double t0, double t1, double max_dt, int T, const double* t_eval, double* out_rho_dev,
                               double* out_pops_dev, cudaStream_t st) {
-  const int d = m->d, ld = (d + 7) & ~7;
+  const int d = m->d, ld = (d / LC_T) * LC_TS;  // 27-column tiles padded to 32 (lb_col)
+  const int tw = LC_T, tpad = LC_TS - LC_T;
   int rc;
   TimeGrid g;
   rc = casq_build_time_grid(t0, t1, max_dt, T, t_eval, m->dt, n_total, &g);
@@ -314,6 +314,9 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   const size_t o_V = off; off = align16(off + (size_t)d * d * 16);
   const size_t o_ph = off; off = align16(off + (size_t)std::max(T, 1) * d * 16);
   const size_t o_G = off; off = align16(off + (size_t)d * ld * 16);
+  bool g_real = true;
+  for (const cplx& gv : cp.G) g_real = g_real && gv.imag() == 0.0;
+  const size_t o_Gre = off; off = align16(off + (g_real ? (size_t)d * ld * 8 : 16));
   const size_t o_pij = off; off = align16(off + pair_ij.size() * sizeof(int));
   const size_t o_ss = off; off = align16(off + cp.slot_start.size() * sizeof(int));
   const size_t o_av = off; off = align16(off + std::max<size_t>(cp.atom_val.size(), 1) * 16);
@@ -334,6 +337,10 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
       }
   }
   memcpy(&blob[o_G], cp.G.data(), (size_t)d * ld * 16);
+  if (g_real) {
+    double* gr = reinterpret_cast<double*>(&blob[o_Gre]);
+    for (size_t i = 0; i < (size_t)d * ld; i++) gr[i] = cp.G[i].real();
+  }
   memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
   memcpy(&blob[o_ss], cp.slot_start.data(), cp.slot_start.size() * sizeof(int));
   if (!cp.atom_val.empty()) {
@@ -386,6 +393,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   c.drv_mask = cp.drv_mask;
   c.pair_ij = (const int*)(dev + o_pij);
   c.G = (const double2*)(dev + o_G);
+  c.Gre = g_real ? (const double*)(dev + o_Gre) : nullptr;
   c.slot_start = (const int*)(dev + o_ss);
   c.atom_val = (const double2*)(dev + o_av);
   c.atom_code = (const int*)(dev + o_ac);
@@ -439,7 +447,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
     Part& P = parts[pi];
     const long long n = P.Bc * (long long)n_per;
     const double2* r0p = (const double2*)rho0_dev + (rho0_batched ? (size_t)P.b0 * n_per : 0);
-    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, r0p, rho0_batched, P.bufs[0]);
+    lindblad_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, r0p, rho0_batched, P.bufs[0], tw, tpad);
     CASQ_CUDA(cudaGetLastError());
   }
   int t_slot = 0;
@@ -449,13 +457,13 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
       if (out_rho_dev) {
         const long long n = P.Bc * (long long)n_per;
         lindblad_copy_out_kernel<<<(unsigned)((n + 255) / 256), 256, 0, P.st>>>(d, ld, P.Bc, P.bufs[0],
-                                                                              (double2*)out_rho_dev + (size_t)P.b0 * T * n_per, T, t_slot);
+                                                                              (double2*)out_rho_dev + (size_t)P.b0 * T * n_per, T, t_slot, tw, tpad);
         CASQ_CUDA(cudaGetLastError());
       }
       if (out_pops_dev) {
         lindblad_pops_kernel<<<dim3((unsigned)d, (unsigned)P.Bc), 256, 0, P.st>>>(d, ld, P.bufs[0], (const double2*)(dev + o_V),
                                                                                 (const double2*)(dev + o_ph) + (size_t)t_slot * d,
-                                                                                out_pops_dev + (size_t)P.b0 * T * d, T, t_slot);
+                                                                                out_pops_dev + (size_t)P.b0 * T * d, T, t_slot, tw, tpad);
         CASQ_CUDA(cudaGetLastError());
       }
     }
@@ -567,7 +575,7 @@ extern "C" int casq_solve_lindblad_rk4(casq_model* m, int n_slots, const casq_pu
   {
     // chains of three-level sites (every casq TransmonModel with >= 3 qubits) take the register-tiled kernel
     Builder probe = bld;
-    const ChainPlan cp = lc_analyze(m, probe, one, (d + 7) & ~7);
+    const ChainPlan cp = lc_analyze(m, probe, one);
     if (cp.ok)
       return lindblad_run_chain(m, cp, probe, KA, active, ds, n_total, B, params_dev, rho0_dev, rho0_batched, t0, t1, max_dt, T,
                                 t_eval, out_rho_dev, out_pops_dev, st);

@@ -23,8 +23,13 @@
 #include "lindblad_stage.cuh"
 
 #define LC_T 27          // tile edge = 3 sites
+#define LC_TS 32         // storage stride of a tile's columns: 27 used + 5 padding, so that every tile row starts on a 128 B line
 #define LC_WARPS 3       // warps per block = per tile pair: warp g owns the rows with x_2 = g
 #define LC_MAXQ 6        // sites
+#ifndef LC_MINBLOCKS
+#define LC_MINBLOCKS 5    // resident blocks per SM the register allocation aims at: 15 warps, 128 registers, no spills
+                         // (4 / 5 / 6 / 7 blocks measured within 2 % of each other: the stage is not occupancy bound)
+#endif
 #define LC_MAX2 8        // two-sided single-site terms
 #define LC_MAXTERMS 32   // gather terms per task
 
@@ -43,6 +48,7 @@ struct LcArgs {
   const int* pair_ij;         // [npairs][2]
   double2* ctab;              // [3][B][NC]
   const double2* G;           // [d][ld]: A_rr + conj(A_cc) + sum over diagonal L_j of l_j(r) conj(l_j(c))
+  const double* Gre;          // the same as reals when every imaginary part is zero (frame = diag(H0)): half the bytes; else NULL
   // coefficient kernel inputs: slot s = sum over atoms [slot_start[s], slot_start[s+1]) of atom_val * tf[atom_code]
   const int* slot_start;
   const double2* atom_val;
@@ -204,8 +210,8 @@ static inline size_t lindblad_chain_smem(int NC) {
 }
 
 template <int NQ, int XLOW>
-__global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(const LcArgs a, int set, const LbStage s) {
-  constexpr int D = lc_pow3(NQ), LD = (D + 7) & ~7;
+__global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_stage_kernel(const LcArgs a, int set, const LbStage s) {
+  constexpr int D = lc_pow3(NQ), LD = (D / LC_T) * LC_TS;  // every 27-column tile starts on a 512 B boundary
   extern __shared__ __align__(16) unsigned char lc_smem[];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int NCs = (a.NC + 1) & ~1;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(
       }
       const int nr = ti % 3, nc = tj % 3;
       if (nr > 1 || nc > 1) continue;
-      lists[2].off[n] = pw * 27 * (LD + 1);
+      lists[2].off[n] = pw * (27 * LD + LC_TS);
       lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
     }
     lists[2].n = n;
@@ -246,13 +252,13 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(
   __syncthreads();
   const long long base = b * (long long)D * LD;
   const double2* in = s.in + base;
-  const long long o0 = (long long)(LC_T * I + 9 * g) * LD + LC_T * J + cl;   // this warp's rows of tile (I, J)
+  const long long o0 = (long long)(LC_T * I + 9 * g) * LD + LC_TS * J + cl;   // this warp's rows of tile (I, J)
   const double2* cJ12 = ct + 4 * NQ + (1 * 2 + 0) * 4;  // J(1, dir, n, m) = cJ12[(dir*2 + n)*2 + m]
   double2 acc[9];
   // seg 0: M_JI = (A rho)[J, I] -> sT;  seg 1: M_IJ (diagonal pair: also -> sT);  seg 2: + two-sided terms of (I, J)
 #pragma unroll 1
   for (int seg = diag ? 1 : 0; seg < 3; seg++) {
-    const double2* p = seg == 0 ? in + (long long)(LC_T * J + 9 * g) * LD + LC_T * I + cl : in + o0;
+    const double2* p = seg == 0 ? in + (long long)(LC_T * J + 9 * g) * LD + LC_TS * I + cl : in + o0;
     if (seg < 2) {
       lc_zero9(acc);
       lc_in_group<NQ, LD, XLOW>(acc, p, ct);
@@ -290,25 +296,39 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(
   // ---- epilogue: k = M_IJ + M_JI^+ + G o rho, RK4 combination, store; the result replaces the consumed sT slot
   if (active) {
     const double2* p = in + o0;
+    const long long ob = base + o0;
+    const double2* yp = s.y + ob;
+    const double2* y1p = s.y1 + ob;
+    const double2* y2p = s.y2 + ob;
+    double2* outp = s.out + ob;
+    const bool greal = a.Gre != nullptr;
     const double2* gp = a.G + o0;
+    const double* grp = greal ? a.Gre + o0 : nullptr;
+    const double h = s.stage == 3 ? s.h : 0.5 * s.h, t3 = 1.0 / 3.0, h6 = s.h * (1.0 / 6.0);
 #pragma unroll
-    for (int t0 = 0; t0 < 9; t0 += 3) {  // three rows at a time: nine independent loads in flight, 36 registers
+    for (int t0 = 0; t0 < 9; t0 += 3) {  // three rows at a time: nine or more independent loads in flight
       double2 y0[3], v[3], gg[3];
 #pragma unroll
       for (int u = 0; u < 3; u++) {
-        y0[u] = s.y[base + o0 + (long long)(t0 + u) * LD];
+        y0[u] = yp[(t0 + u) * LD];
         v[u] = __ldg(p + (t0 + u) * LD);
-        gg[u] = __ldg(gp + (t0 + u) * LD);
+        gg[u] = greal ? make_double2(__ldg(grp + (t0 + u) * LD), 0.0) : __ldg(gp + (t0 + u) * LD);
       }
 #pragma unroll
       for (int u = 0; u < 3; u++) {
         const int t = t0 + u;
-        const long long o = base + o0 + (long long)t * LD;
         const double2 m = sT[lane * LC_T + 9 * g + t];  // M_JI(J*27 + lane, I*27 + 9g + t)
         double2 k = make_double2(acc[t].x + m.x, acc[t].y - m.y);
         lc_cfma(k, gg[u], v[u]);
-        const double2 res = lb_rk4_combine(s, o, y0[u], k.x, k.y);
-        s.out[o] = res;
+        double2 res;
+        if (s.stage != 4) {
+          res = make_double2(fma(h, k.x, y0[u].x), fma(h, k.y, y0[u].y));
+        } else {  // y <- (y1 + 2 y2 + y3 - y)/3 + h/6 k4 (v = y3 is the stage input)
+          const double2 v1 = y1p[t * LD], v2 = y2p[t * LD];
+          res = make_double2(fma(h6, k.x, t3 * (v1.x + 2.0 * v2.x + v[u].x - y0[u].x)),
+                             fma(h6, k.y, t3 * (v1.y + 2.0 * v2.y + v[u].y - y0[u].y)));
+        }
+        outp[t * LD] = res;
         if (!diag) sT[lane * LC_T + 9 * g + t] = res;
       }
     }
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, 6) lindblad_chain_stage_kernel(
   __syncthreads();
   // ---- mirror tile: out(J*27 + r, I*27 + lane) = conj(out(I*27 + lane, J*27 + r)) = conj(sT[r][lane]), r = 9g + t
   if (active) {
-    const long long om = base + (long long)(LC_T * J + 9 * g) * LD + LC_T * I + lane;
+    const long long om = base + (long long)(LC_T * J + 9 * g) * LD + LC_TS * I + lane;
 #pragma unroll
     for (int t = 0; t < 9; t++) {
       const double2 r = sT[(9 * g + t) * LC_T + lane];

@@ -135,21 +135,25 @@ struct LbStage {
 };
 
 // rho0 broadcast / copy into the (row-padded) working buffer
+// Column c of a density matrix sits at storage column lb_col(c): the generic path stores rows contiguously (tpad = 0), the
+// chain path pads every 27-column tile to 32 (tw = 27, tpad = 5) so that tile rows are 128 B aligned.
+__device__ __forceinline__ int lb_col(int c, int tw, int tpad) { return tpad ? c + (c / tw) * tpad : c; }
+
 __global__ void lindblad_init_kernel(int d, int ld, long long B, const double2* __restrict__ rho0, int batched,
-                                     double2* __restrict__ y) {
+                                     double2* __restrict__ y, int tw = 1, int tpad = 0) {
   const long long n_per = (long long)d * d;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_per * B) return;
   const long long b = i / n_per, e = i - b * n_per;
   const int r = (int)(e / d), c = (int)(e - (long long)r * d);
-  y[(b * d + r) * ld + c] = batched ? rho0[i] : rho0[e];
+  y[(b * d + r) * ld + lb_col(c, tw, tpad)] = batched ? rho0[i] : rho0[e];
 }
 
 // Observables at one output time: dressed-basis populations p_i = (V^+ rho_lab V)_ii with
 // rho_lab[a,b] = e^{-i(e_a-e_b)t} rho_F[a,b].  One block per (state i, trajectory b).
 __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, int ld, const double2* __restrict__ rho, const double2* __restrict__ V,
                                                             const double2* __restrict__ ph /*[d] e^{-i e t}*/,
-                                                            double* __restrict__ pops, int T, int t_slot) {
+                                                            double* __restrict__ pops, int T, int t_slot, int tw = 1, int tpad = 0) {
   const int i = blockIdx.x;
   const long long b = blockIdx.y;
   const double2* R = rho + b * (long long)d * ld;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, int ld, const
     for (int bc = 0; bc < d; bc++) {
       const double2 v = V[bc * d + i], p = ph[bc];
       const double2 w = make_double2(v.x * p.x + v.y * p.y, v.y * p.x - v.x * p.y);  // V[b,i] conj(ph_b)
-      const double2 x = R[(long long)arow * ld + bc];
+      const double2 x = R[(long long)arow * ld + lb_col(bc, tw, tpad)];
       sx += x.x * w.x - x.y * w.y;
       sy += x.x * w.y + x.y * w.x;
     }
@@ -178,11 +182,11 @@ __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, int ld, const
 }
 
 __global__ void lindblad_copy_out_kernel(int d, int ld, long long B, const double2* __restrict__ y, double2* __restrict__ out,
-                                         int T, int t_slot) {
+                                         int T, int t_slot, int tw = 1, int tpad = 0) {
   const long long n_per = (long long)d * d;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_per * B) return;
   const long long b = i / n_per, e = i - b * n_per;
   const int r = (int)(e / d), c = (int)(e - (long long)r * d);
-  out[(b * T + t_slot) * n_per + e] = y[(b * d + r) * ld + c];
+  out[(b * T + t_slot) * n_per + e] = y[(b * d + r) * ld + lb_col(c, tw, tpad)];
 }
