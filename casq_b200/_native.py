@@ -16,7 +16,7 @@ import os
 _LIB_PATH = Path(os.environ.get("CASQ_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libcasq_b200.so")
 _lib = None
 
-NPARAM = 5
+NPARAM = 6
 MAX_SLOTS = 4
 PULSE_KINDS = {"constant": 0, "gaussian": 1, "drag": 2, "gaussian_square": 3, "gaussian_square_drag": 4}
 
@@ -35,7 +35,7 @@ _SIGNATURES = {
     "casq_model_get": (C.c_int, [_P, _P, _P, _P, _P]),
     "casq_model_dim": (C.c_int, [_P]),
     "casq_model_invalidate_cache": (C.c_int, [_P]),
-    "casq_envelope_sample": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P, _P]),
+    "casq_envelope_sample": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, C.c_int, C.c_double, _P, _P]),
     "casq_solve_sv_rk4": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,
                                     C.c_double, C.c_int, _P, _P, _P]),
     "casq_solve_sv_dopri5": (C.c_int, [_P, C.c_int, C.POINTER(PulseSlot), C.c_int64, _P, _P, C.c_int, C.c_double, C.c_double,

@@ -23,7 +23,7 @@ from ...gates.pulse_circuit import PulseCircuit
 from ...gates.pulse_gate import PulseGate
 from ...models.control_model import ControlModel
 from ...models.hamiltonian_model import HamiltonianModel
-from ...pulse import Play, Schedule
+from ...pulse import Play, Schedule, SetFrequency, SetPhase, ShiftFrequency, ShiftPhase
 from ...quantum_info import DensityMatrix, Statevector
 from ..pulse_backend import PulseBackend
 
@@ -50,6 +50,38 @@ class BatchSolution:
     @property
     def batch_size(self) -> int:
         return int(self.states.shape[0])
+
+
+@dataclass
+class DurationSweepSolution:
+    """Result of ``solve_batch(duration=[...])``: points of different gate duration have different time grids, so ``times``
+    is per point: times [B, T], states [B, T, d], probabilities [B, T, d], populations [B, T, 2]."""
+
+    times: np.ndarray
+    states: torch.Tensor
+    probabilities: torch.Tensor
+    populations: torch.Tensor
+    durations: np.ndarray
+
+    @property
+    def batch_size(self) -> int:
+        return int(self.states.shape[0])
+
+    @staticmethod
+    def assemble(B: int, parts: dict) -> "DurationSweepSolution":
+        first = next(iter(parts.values()))[1]
+        T, d, dev = first.states.shape[1], first.states.shape[2], first.states.device
+        times = np.zeros((B, T))
+        states = torch.empty((B, T, d), dtype=torch.complex128, device=dev)
+        probs = torch.empty((B, T, d), dtype=torch.float64, device=dev)
+        pops = torch.empty((B, T, 2), dtype=torch.float64, device=dev)
+        durs = np.zeros(B, dtype=np.int64)
+        for dur, (sel, sol) in parts.items():
+            idx = torch.as_tensor(sel, device=dev)
+            times[sel] = sol.times
+            states[idx], probs[idx], pops[idx] = sol.states, sol.probabilities, sol.populations
+            durs[sel] = dur
+        return DurationSweepSolution(times=times, states=states, probabilities=probs, populations=pops, durations=durs)
 
 
 class B200PulseBackend(PulseBackend):
@@ -124,13 +156,38 @@ class B200PulseBackend(PulseBackend):
         return sched, t_acq, measured
 
     def _slots_from_schedule(self, sched: Schedule):
+        """Play instructions -> engine slots.  Phase / frequency instructions act on the LATER plays of their channel, as in
+        qiskit-dynamics' InstructionToSignals: the accumulated phase joins the pulse angle, the
+        accumulated frequency shift becomes the slot's freq_shift."""
         slots, params = [], []
-        for start, inst in sched.plays():
-            name = inst.channel.name
+        phase: dict = {}
+        fshift: dict = {}
+        for start, inst in sorted(sched.instructions, key=lambda si: si[0]):
+            ch = getattr(inst, "channel", None)
+            name = ch.name if ch is not None else None
+            if isinstance(inst, ShiftPhase):
+                phase[name] = phase.get(name, 0.0) + inst.phase
+                continue
+            if isinstance(inst, SetPhase):
+                phase[name] = inst.phase
+                continue
+            if isinstance(inst, ShiftFrequency):
+                fshift[name] = fshift.get(name, 0.0) + inst.frequency
+                continue
+            if isinstance(inst, SetFrequency):
+                fshift[name] = inst.frequency - (self.control.channel_carrier_freqs or {}).get(name, 0.0)
+                continue
+            if not isinstance(inst, Play):
+                continue
             if name not in self.hamiltonian.channels:
                 raise CasqError(f"Schedule plays on channel '{name}' which is not in the Hamiltonian model {self.hamiltonian.channels}.")
             slots.append((inst.pulse.kind, self.hamiltonian.channels.index(name), start, inst.pulse.duration))
-            params.append(inst.pulse.engine_params())
+            ep = inst.pulse.engine_params()
+            if phase.get(name):
+                ep["angle"] = np.asarray(ep.get("angle", 0.0), dtype=float) + phase[name]
+            if fshift.get(name):
+                ep["freq_shift"] = fshift[name]
+            params.append(ep)
         if len(slots) > 4:
             raise CasqError(f"At most 4 Play instructions per schedule are supported, got {len(slots)}.")
         return slots, params
@@ -209,25 +266,59 @@ class B200PulseBackend(PulseBackend):
 
     def solve_batch(self, gate: PulseGate, parameters: Union[dict, np.ndarray], method: "PulseBackend.ODESolverMethod",
                     qubit: int = 0, amplitude=None, angle=None, initial_state=None, steps: Optional[int] = None,
-                    run_options: Optional[dict] = None, keep_raw: bool = False) -> BatchSolution:
+                    run_options: Optional[dict] = None, keep_raw: bool = False, detuning=None, duration=None,
+                    channel: Optional[str] = None) -> BatchSolution:
         """Sweep / candidate batch for one gate: ``parameters`` is a dict of arrays (e.g. {"sigma": [B],
         "beta": [B]}) or a [B, P] array in ``gate.to_parameters_dict`` order; ``amplitude``/``angle`` may be
-        arrays too (default: the gate's own).  Reduces to ``solve`` semantics for B = 1."""
+        arrays too (default: the gate's own).  Reduces to ``solve`` semantics for B = 1.
+
+        ``detuning`` (Hz, scalar or [B]): per-point frequency shift of the drive, i.e. a ShiftFrequency in front of the
+        Play (samples times exp(i 2 pi detuning dt n)) -- one launch for the whole sweep.
+        ``duration`` (samples, scalar or [B] integers): per-point gate duration (PulseGate.duration, pulse_gate.py:69-72).
+        The duration fixes t_span = [0, duration dt] (dynamics_backend_patch.py:180-184) and with it the solver's time
+        grid, so the batch runs as one launch per distinct duration, each on exactly the grid the reference would use for
+        that duration; the result is a ``DurationSweepSolution`` (per-point times)."""
         if not isinstance(parameters, dict):
             arr = np.atleast_2d(np.asarray(parameters, dtype=float))
             parameters = gate.to_parameters_dict(arr.T)
         amp = gate.amplitude if amplitude is None else amplitude
         ang = gate.angle if angle is None else angle
-        pulse = type(gate.pulse({k: np.asarray(v, dtype=float) for k, v in parameters.items()}))(
-            duration=gate.duration, amp=np.asarray(amp, dtype=float), angle=0.0 if ang is None else np.asarray(ang, dtype=float),
-            limit_amplitude=gate.limit_amplitude, name=gate.name, **{k: np.asarray(v, dtype=float) for k, v in parameters.items()})
-        name = f"d{qubit}"
+        name = channel if channel is not None else gate.channel_name(qubit)
         if name not in self.hamiltonian.channels:
-            raise CasqError(f"DriveChannel({qubit}) ('{name}') is not in the Hamiltonian model {self.hamiltonian.channels}.")
-        slots = [(pulse.kind, self.hamiltonian.channels.index(name), 0, pulse.duration)]
+            raise CasqError(f"Channel '{name}' is not in the Hamiltonian model {self.hamiltonian.channels}.")
         m = method.value if isinstance(method, PulseBackend.ODESolverMethod) else str(method)
-        return self.solve_slots_batch(slots, [pulse.engine_params()], pulse.duration, m, initial_state, steps,
-                                      run_options, keep_raw)
+        kw = {k: np.asarray(v, dtype=float) for k, v in parameters.items()}
+
+        def build(dur, sel=None):
+            pick = (lambda v: v) if sel is None else (lambda v: v[sel] if np.ndim(v) > 0 else v)
+            pulse = type(gate.pulse({k: pick(v) for k, v in kw.items()}))(
+                duration=int(dur), amp=pick(np.asarray(amp, dtype=float)),
+                angle=0.0 if ang is None else pick(np.asarray(ang, dtype=float)),
+                limit_amplitude=gate.limit_amplitude, name=gate.name, **{k: pick(v) for k, v in kw.items()})
+            ep = pulse.engine_params()
+            if detuning is not None:
+                ep["freq_shift"] = pick(np.asarray(detuning, dtype=float))
+            return pulse, ep
+
+        if duration is None or np.ndim(duration) == 0:
+            pulse, ep = build(gate.duration if duration is None else duration)
+            slots = [(pulse.kind, self.hamiltonian.channels.index(name), 0, pulse.duration)]
+            return self.solve_slots_batch(slots, [ep], pulse.duration, m, initial_state, steps, run_options, keep_raw)
+        durations = np.asarray(duration)
+        if not np.all(durations == np.round(durations)) or np.any(durations < 1):
+            raise CasqError("Per-point durations must be positive integers (samples).")
+        durations = durations.astype(np.int64)
+        B = len(durations)
+        parts = {}
+        for dur in np.unique(durations):
+            sel = np.nonzero(durations == dur)[0]
+            pulse, ep = build(dur, sel)
+            slots = [(pulse.kind, self.hamiltonian.channels.index(name), 0, pulse.duration)]
+            y0 = initial_state
+            if y0 is not None and np.ndim(getattr(y0, "data", y0)) == 2 and np.shape(getattr(y0, "data", y0))[0] == B:
+                y0 = np.asarray(getattr(y0, "data", y0))[sel]
+            parts[int(dur)] = (sel, self.solve_slots_batch(slots, [ep], int(dur), m, y0, steps, run_options, keep_raw))
+        return DurationSweepSolution.assemble(B, parts)
 
     # ------------------------------------------------------------------ the drop-in call
     def solve(

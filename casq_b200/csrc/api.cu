@@ -17,26 +17,28 @@ int casq_general_rk4(casq_model* m, int KA, const int* active, const DevSlots& s
 
 // ---------------------------------------------------------------------------------------------
 // stand-alone envelope sampler
-__global__ void envelope_sample_kernel(int kind, int duration, long long B, const double* __restrict__ params,
-                                       double* __restrict__ out) {
+__global__ void envelope_sample_kernel(int kind, int duration, long long B, const double* __restrict__ params, int start,
+                                       double dt, double* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * duration) return;
   const long long b = i / duration;
   const int n = (int)(i - b * duration);
   dcplx e = casq_envelope_eval(kind, duration, n, params[b], params[B + b], params[2 * B + b], params[3 * B + b],
                                params[4 * B + b]);
+  const double fs = params[5 * B + b];
+  if (fs != 0.0) e = casq_apply_freq_shift(e, fs, dt, start + n);
   reinterpret_cast<double2*>(out)[i] = make_double2(e.re, e.im);
 }
 
-extern "C" int casq_envelope_sample(int kind, int duration, int64_t B, const double* params_dev, double* out_dev,
-                                    void* stream) {
+extern "C" int casq_envelope_sample(int kind, int duration, int64_t B, const double* params_dev, int start, double dt,
+                                    double* out_dev, void* stream) {
   if (kind < 0 || kind > CASQ_PULSE_GAUSSIAN_SQUARE_DRAG) CASQ_FAIL(CASQ_ERR_INVALID, "unknown pulse kind %d", kind);
   if (duration < 1 || B < 0) CASQ_FAIL(CASQ_ERR_INVALID, "casq_envelope_sample: bad arguments");
   if (B == 0) return CASQ_OK;
   if (!params_dev || !out_dev) CASQ_FAIL(CASQ_ERR_INVALID, "casq_envelope_sample: NULL buffer");
   const long long n = (long long)B * duration;
   envelope_sample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, duration, B, params_dev,
-                                                                                       out_dev);
+                                                                                       start, dt, out_dev);
   CASQ_CUDA(cudaGetLastError());
   return CASQ_OK;
 }
@@ -50,6 +52,7 @@ int casq_prepare_slots(const casq_model* m, int n_slots, const casq_pulse_slot* 
   if (n_slots > 0 && !slots) CASQ_FAIL(CASQ_ERR_INVALID, "slots is NULL");
   memset(ds, 0, sizeof(*ds));
   ds->n = n_slots;
+  ds->dt = m->dt;
   *n_active = 0;
   *n_total = 0;
   for (int i = 0; i < n_slots; i++) {

@@ -54,9 +54,21 @@ __device__ __forceinline__ dcplx casq_envelope_eval(int kind, int duration, int 
   return out;
 }
 
+// Per-point detuning: samples of a frequency-shifted channel carry exp(i 2 pi freq_shift dt n), n = global sample index
+// (InstructionToSignals: times = dt * (start_sample + arange(n_samples))).
+__device__ __forceinline__ dcplx casq_apply_freq_shift(dcplx e, double freq_shift, double dt, int gidx) {
+  double sn, cs;
+  sincos(6.283185307179586 * freq_shift * (dt * (double)gidx), &sn, &cs);
+  dcplx o;
+  o.re = e.re * cs - e.im * sn;
+  o.im = e.re * sn + e.im * cs;
+  return o;
+}
+
 // Slots as the kernels see them: `channel` already remapped to the ACTIVE channel index.
 struct DevSlots {
   int n;
+  double dt;  // sample period (the phase of a per-point frequency shift advances by 2 pi freq_shift dt per sample)
   int kind[CASQ_MAX_SLOTS], ach[CASQ_MAX_SLOTS], start[CASQ_MAX_SLOTS], duration[CASQ_MAX_SLOTS];
 };
 
@@ -71,6 +83,8 @@ __device__ __forceinline__ void casq_channel_envelopes(const DevSlots& s, const 
     if (n < 0 || n >= s.duration[i]) continue;
     const double* p = params + (long long)i * CASQ_NPARAM * B + b;
     dcplx e = casq_envelope_eval(s.kind[i], s.duration[i], n, p[0], p[B], p[2 * B], p[3 * B], p[4 * B]);
+    const double fs = p[5 * B];
+    if (fs != 0.0) e = casq_apply_freq_shift(e, fs, s.dt, gidx);
 #pragma unroll
     for (int k = 0; k < KA; k++)
       if (s.ach[i] == k) {

@@ -13,7 +13,7 @@ import torch
 from . import _native
 from .common.exceptions import CasqError
 
-PARAM_ORDER = ("amp", "angle", "sigma", "width", "beta")
+PARAM_ORDER = ("amp", "angle", "sigma", "width", "beta", "freq_shift")
 
 
 def _require_cuda(device) -> torch.device:
@@ -27,9 +27,9 @@ def _stream_ptr(dev: torch.device) -> int:
 
 
 def pack_params(slot_params: Sequence[dict], batch: Optional[int] = None, device=None, pin: bool = False) -> torch.Tensor:
-    """Build the SoA parameter block [n_slots, 5, B] (float64) from per-slot dicts.
+    """Build the SoA parameter block [n_slots, 6, B] (float64) from per-slot dicts.
 
-    Each dict maps amp/angle/sigma/width/beta to a scalar or a length-B array; missing entries are 0
+    Each dict maps amp/angle/sigma/width/beta/freq_shift (Hz) to a scalar or a length-B array; missing entries are 0
     (angle None -> 0, like qiskit's symbolic pulses).  Returned on `device` when given, else on the host
     (pinned when `pin`).
     """
@@ -56,19 +56,21 @@ def pack_params(slot_params: Sequence[dict], batch: Optional[int] = None, device
     return host if device is None else host.to(device, non_blocking=True)
 
 
-def envelope_sample(kind, duration: int, params: torch.Tensor) -> torch.Tensor:
-    """samples[b, n] = envelope(n + 1/2) on the device.  params: CUDA float64 [5, B] (one slot)."""
+def envelope_sample(kind, duration: int, params: torch.Tensor, start: int = 0, dt: float = 0.0) -> torch.Tensor:
+    """samples[b, n] = envelope(n + 1/2) on the device.  params: CUDA float64 [6, B] (one slot); `start` and `dt` only
+    matter for points with a frequency shift (phase exp(i 2 pi freq_shift dt (start + n)))."""
     if not params.is_cuda:
         raise CasqError("envelope_sample: params must be a CUDA tensor")
     params = params.contiguous()
     if params.dim() != 2 or params.shape[0] != _native.NPARAM or params.dtype != torch.float64:
-        raise CasqError("envelope_sample: params must be float64 [5, B]")
+        raise CasqError("envelope_sample: params must be float64 [6, B]")
     B = params.shape[1]
     out = torch.empty((B, duration), dtype=torch.complex128, device=params.device)
     k = _native.PULSE_KINDS[kind] if isinstance(kind, str) else int(kind)
     with torch.cuda.device(params.device):
         _native.check(
-            _native.load().casq_envelope_sample(k, int(duration), B, params.data_ptr(), out.data_ptr(), _stream_ptr(params.device)),
+            _native.load().casq_envelope_sample(k, int(duration), B, params.data_ptr(), int(start), float(dt), out.data_ptr(),
+                                                _stream_ptr(params.device)),
             "casq_envelope_sample",
         )
     return out
@@ -79,12 +81,12 @@ def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_
     """Fixed-step RK4 for a batch of pulse points.  Returns CUDA complex128 [B, T, d]: the states
     Solver.solve returns (rotating frame, lab basis) at t_eval (or at the two ends of t_span).
 
-    slots: [(kind, channel_index, start, duration)]; params: CUDA float64 [n_slots, 5, B];
+    slots: [(kind, channel_index, start, duration)]; params: CUDA float64 [n_slots, 6, B];
     y0: [d] or [B, d] (numpy or torch, lab basis).
     """
     dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
     if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("solve_sv_rk4: params must be a CUDA float64 tensor [n_slots, 5, B]")
+        raise CasqError("solve_sv_rk4: params must be a CUDA float64 tensor [n_slots, 6, B]")
     params = params.contiguous()
     slots = list(slots)
     if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
@@ -118,7 +120,7 @@ def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_
 def _prep_solve(model, slots, params, y0, t_eval, what):
     dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
     if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError(f"{what}: params must be a CUDA float64 tensor [n_slots, 5, B]")
+        raise CasqError(f"{what}: params must be a CUDA float64 tensor [n_slots, 6, B]")
     params = params.contiguous()
     slots = list(slots)
     if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
@@ -164,7 +166,7 @@ def propagators_expm(model: _native.NativeModel, slots, params: torch.Tensor, t_
     (rotating frame, lab basis).  One expm (scaling-and-squaring Pade) per step of the fixed-step grid."""
     dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
     if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("propagators_expm: params must be a CUDA float64 tensor [n_slots, 5, B]")
+        raise CasqError("propagators_expm: params must be a CUDA float64 tensor [n_slots, 6, B]")
     params = params.contiguous()
     slots = list(slots)
     if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
@@ -189,7 +191,7 @@ def solve_lindblad_rk4(model: _native.NativeModel, slots, params: torch.Tensor, 
     frame or None, pops [B,T,d] dressed-basis populations after frame removal or None)."""
     dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
     if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("solve_lindblad_rk4: params must be a CUDA float64 tensor [n_slots, 5, B]")
+        raise CasqError("solve_lindblad_rk4: params must be a CUDA float64 tensor [n_slots, 6, B]")
     params = params.contiguous()
     slots = list(slots)
     if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):

@@ -50,10 +50,14 @@ class PulseCircuit:
     def add_calibration(self, gate_name: str, qubits, schedule: Schedule, params=None) -> None:
         self.calibrations.setdefault(gate_name, {})[(tuple(qubits), tuple(params or ()))] = schedule
 
-    def pulse_gate(self, gate: PulseGate, parameters: dict[str, Any], qubit: int = 0) -> CircuitInstruction:
-        """Append the gate and attach its schedule as the calibration (pulse_circuit.py:81-98)."""
-        inst = self.append(gate, [qubit])
-        self.add_calibration(gate.name, [qubit], gate.schedule(parameters, qubit), [])
+    def pulse_gate(self, gate: PulseGate, parameters: dict[str, Any], qubit=0) -> CircuitInstruction:
+        """Append the gate and attach its schedule as the calibration (pulse_circuit.py:81-98).  ``qubit`` is an int for
+        casq's single-qubit gates; a multi-qubit gate (CrossResonancePulseGate) takes a sequence (control, target)."""
+        qubits = [qubit] if isinstance(qubit, int) else [int(q) for q in qubit]
+        if len(qubits) != gate.num_qubits:
+            raise CasqError(f"Gate '{gate.name}' acts on {gate.num_qubits} qubit(s), got {qubits}.")
+        inst = self.append(gate, qubits)
+        self.add_calibration(gate.name, qubits, gate.schedule(parameters, qubits[0]), [])
         return inst
 
     def measure(self, qubit: int, clbit: int) -> CircuitInstruction:

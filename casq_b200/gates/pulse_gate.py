@@ -37,8 +37,16 @@ class PulseGate(ABC):
     def to_parameters_dict(self, parameters: npt.NDArray) -> dict[str, Any]:
         """Builds the parameter dictionary from an array of parameter values."""
 
+    def channel(self, qubit: int):
+        """The channel the gate plays on: DriveChannel(qubit) for every casq gate (pulse_gate.py:111); multi-qubit gates
+        (CrossResonancePulseGate) override it with their ControlChannel."""
+        return DriveChannel(qubit)
+
+    def channel_name(self, qubit: int) -> str:
+        return self.channel(qubit).name
+
     def schedule(self, parameters: dict[str, Any], qubit: int) -> Schedule:
         """One-instruction schedule playing the gate's pulse on DriveChannel(qubit) (pulse_gate.py:97-112)."""
         sched = Schedule(name=f"{self.name}Schedule")
-        sched.insert(0, Play(self.pulse(parameters), DriveChannel(qubit)))
+        sched.insert(0, Play(self.pulse(parameters), self.channel(qubit)))
         return sched

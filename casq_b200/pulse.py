@@ -122,6 +122,41 @@ class Play:
 
 
 @dataclass
+class ShiftFrequency:
+    """qiskit.pulse.ShiftFrequency: later Plays on `channel` are detuned by `frequency` Hz (accumulates).  casq's own gates
+    never emit it; it is what a per-point detuning of ``solve_batch`` means for a single circuit."""
+
+    frequency: float
+    channel: Channel
+    duration: int = 0
+
+
+@dataclass
+class SetFrequency:
+    """qiskit.pulse.SetFrequency: later Plays on `channel` run at `frequency` Hz (shift = frequency - carrier)."""
+
+    frequency: float
+    channel: Channel
+    duration: int = 0
+
+
+@dataclass
+class ShiftPhase:
+    """qiskit.pulse.ShiftPhase: later Plays on `channel` are multiplied by exp(i phase) (accumulates)."""
+
+    phase: float
+    channel: Channel
+    duration: int = 0
+
+
+@dataclass
+class SetPhase:
+    phase: float
+    channel: Channel
+    duration: int = 0
+
+
+@dataclass
 class Acquire:
     duration: int
     qubit: int

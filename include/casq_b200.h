@@ -47,8 +47,14 @@ typedef enum {
 } casq_pulse_kind;
 
 /* Per-point pulse parameters are a structure-of-arrays block of CASQ_NPARAM rows per slot:
- *   params_dev[(slot*CASQ_NPARAM + j)*B + b],  j = 0 amp, 1 angle, 2 sigma, 3 width, 4 beta. */
-#define CASQ_NPARAM 5
+ *   params_dev[(slot*CASQ_NPARAM + j)*B + b],  j = 0 amp, 1 angle, 2 sigma, 3 width, 4 beta, 5 freq_shift (Hz).
+ * freq_shift is the per-point detuning of the Play instruction: qiskit-dynamics' InstructionToSignals multiplies the
+ * samples of a channel whose frequency was shifted (ShiftFrequency / SetFrequency before the Play) by
+ * exp(i 2 pi freq_shift dt n), n = the GLOBAL sample index (the code casq calls at src/casq/common/helpers.py:124-132);
+ * 0 = no shift.  Per-point DURATION is not a row: the duration fixes t_span (PulseGate.duration,
+ * src/casq/gates/pulse_gate.py:69-72 -> dynamics_backend_patch.py:180-184) and with it the fixed-step grid, so points of
+ * different duration run as one launch per distinct duration (casq_b200.backends.b200: solve_batch(duration=[...])). */
+#define CASQ_NPARAM 6
 #define CASQ_MAX_SLOTS 4
 
 /* One Play instruction of the schedule (PulseGate.schedule, src/casq/gates/pulse_gate.py:97-112):
@@ -97,7 +103,8 @@ int casq_model_invalidate_cache(casq_model* m);
 /* ---- envelope sampler -------------------------------------------------------------------------
  * Replaces the per-solve InstructionToSignals.get_signals sampling (same code casq calls at
  * src/casq/common/helpers.py:124-127): out_dev[b*duration + n] = envelope(n + 1/2; params of point b). */
-int casq_envelope_sample(int kind, int duration, int64_t B, const double* params_dev /*[5*B] SoA*/,
+int casq_envelope_sample(int kind, int duration, int64_t B, const double* params_dev /*[CASQ_NPARAM*B] SoA*/,
+                         int start /* first global sample of the Play (phase of a frequency shift) */, double dt,
                          double* out_dev /*[B*duration] c128*/, void* stream);
 
 /* ---- state-vector solves ----------------------------------------------------------------------

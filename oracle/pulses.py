@@ -69,11 +69,14 @@ class PulseSpec:
     start: int = 0
 
 
-def channel_samples(model_channels, specs, params, total_duration=None):
+def channel_samples(model_channels, specs, params, total_duration=None, dt=None):
     """InstructionToSignals.get_signals restated: one complex sample array per Hamiltonian channel.
 
-    specs: list[PulseSpec]; params: list of dicts (amp, angle, sigma, width, beta), each value a
+    specs: list[PulseSpec]; params: list of dicts (amp, angle, sigma, width, beta, freq_shift), each value a
     scalar or [B] array.  Returns samples [B, K, N] (zeros where nothing is played).
+    freq_shift (Hz, needs ``dt``): the frequency shift accumulated on the channel before the Play
+    (ShiftFrequency / SetFrequency); upstream multiplies the played samples by
+    exp(2j pi freq_shift * dt * (start_sample + arange(n_samples))) -- SURVEY Appendix A.3.
     """
     B = 1
     for p in params:
@@ -84,8 +87,14 @@ def channel_samples(model_channels, specs, params, total_duration=None):
     out = np.zeros((B, len(model_channels), N), dtype=complex)
     for s, p in zip(specs, params):
         k = list(model_channels).index(s.channel)
-        env = envelope_samples(s.kind, s.duration, **{kk: vv for kk, vv in p.items()})
+        env = envelope_samples(s.kind, s.duration, **{kk: vv for kk, vv in p.items() if kk != "freq_shift"})
         env = np.broadcast_to(env, (B, s.duration)) if env.ndim > 1 else np.broadcast_to(env[None], (B, s.duration))
+        fs = p.get("freq_shift")
+        if fs is not None and np.any(np.asarray(fs) != 0):
+            if dt is None:
+                raise ValueError("freq_shift needs dt")
+            times = dt * (s.start + np.arange(s.duration, dtype=float))
+            env = env * np.exp(2j * np.pi * np.asarray(fs, dtype=float).reshape(-1, 1) * times)
         out[:, k, s.start : s.start + s.duration] += env
     return out
 

@@ -70,7 +70,7 @@ def test_model_create_rejects_bad_arguments(native_lib):
     rc = native_lib.casq_model_create(ctypes.byref(h), 0, 0, None, None, None, 1e-10, 0, None, math.nan, 0)
     assert rc == -1 and b"dim" in native_lib.casq_last_error()
     assert native_lib.casq_model_invalidate_cache(None) == -1
-    assert native_lib.casq_envelope_sample(9, 16, 4, None, None, None) == -1 and b"kind" in native_lib.casq_last_error()
+    assert native_lib.casq_envelope_sample(9, 16, 4, None, 0, 0.0, None, None) == -1 and b"kind" in native_lib.casq_last_error()
 
 
 def test_rwa_masks_match_oracle(native_lib):

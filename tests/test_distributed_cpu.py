@@ -26,7 +26,7 @@ def _worker(rank, world, port, total, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        params = torch.arange(5 * total, dtype=torch.float64).reshape(1, 5, total)
+        params = torch.arange(6 * total, dtype=torch.float64).reshape(1, 6, total)
         mine = shard_last_dim(params, rank, world)
         lo, hi = shard_bounds(total, rank, world)
         assert mine.shape[-1] == hi - lo
@@ -53,7 +53,7 @@ def test_two_rank_gloo_shard_and_gather(total):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    params = torch.arange(5 * total, dtype=torch.float64).reshape(1, 5, total)
+    params = torch.arange(6 * total, dtype=torch.float64).reshape(1, 6, total)
     want = torch.complex(params[0, 0], params[0, 4]).reshape(-1, 1, 1).repeat(1, 2, 3)
     for rank, full, only0 in results:
         assert torch.equal(full, want)

@@ -22,7 +22,7 @@ def q0():
 
 def test_empty_batches(q0):
     om, nm, ch = q0
-    empty = torch.zeros((1, 5, 0), dtype=torch.float64, device="cuda")
+    empty = torch.zeros((1, 6, 0), dtype=torch.float64, device="cuda")
     slots = [("drag", 0, 0, 16)]
     assert engine.solve_sv_rk4(nm, slots, empty, np.array([1, 0, 0]), (0, 16 * DT), DT / 10).shape == (0, 2, 3)
     assert engine.solve_sv_dopri5(nm, slots, empty, np.array([1, 0, 0]), (0, 16 * DT)).shape == (0, 2, 3)
@@ -53,7 +53,7 @@ def test_rk4_chunk_boundaries_and_single_output(q0, n_steps_per_piece):
 
 def test_free_evolution_is_identity_in_the_h0_frame(q0):
     om, nm, ch = q0
-    params = torch.zeros((1, 5, 3), dtype=torch.float64, device="cuda")
+    params = torch.zeros((1, 6, 3), dtype=torch.float64, device="cuda")
     y0 = np.array([0.6, 0.0, 0.8j])
     out = engine.solve_sv_rk4(nm, [], params, y0, (0.0, 40 * DT), DT / 10)
     assert np.abs(out.cpu().numpy()[:, -1] - y0).max() < 1e-15

@@ -66,7 +66,7 @@ def test_envelope_sampler_golden_and_edge_cases():
         assert np.abs(got - O.envelope_samples("gaussian_square", 16, **p)).max() < 1e-15
     one = engine.envelope_sample("gaussian", 1, engine.pack_params([dict(amp=0.3, sigma=2.0)], device="cuda")[0])
     assert np.abs(one.cpu().numpy() - O.envelope_samples("gaussian", 1, amp=0.3, sigma=2.0)).max() < 1e-15
-    empty = engine.envelope_sample("gaussian", 4, torch.zeros((5, 0), dtype=torch.float64, device="cuda"))
+    empty = engine.envelope_sample("gaussian", 4, torch.zeros((6, 0), dtype=torch.float64, device="cuda"))
     assert empty.shape == (0, 4)
 
 

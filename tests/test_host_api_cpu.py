@@ -137,7 +137,7 @@ def test_pack_params_layout():
     from casq_b200 import engine
 
     t = engine.pack_params([dict(amp=np.array([0.1, 0.2, 0.3]), angle=None, sigma=4.0, beta=np.array([1.0, 2.0, 3.0]))])
-    assert t.shape == (1, 5, 3)
+    assert t.shape == (1, 6, 3) and t[0, 5].tolist() == [0, 0, 0]
     assert t[0, 0].tolist() == [0.1, 0.2, 0.3] and t[0, 1].tolist() == [0, 0, 0] and t[0, 2].tolist() == [4, 4, 4]
     assert t[0, 3].tolist() == [0, 0, 0] and t[0, 4].tolist() == [1, 2, 3]
     with pytest.raises(CasqError, match="inconsistent"):
