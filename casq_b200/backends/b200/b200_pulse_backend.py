@@ -24,7 +24,7 @@ from ...gates.pulse_gate import PulseGate
 from ...models.control_model import ControlModel
 from ...models.hamiltonian_model import HamiltonianModel
 from ...pulse import Play, Schedule, SetFrequency, SetPhase, ShiftFrequency, ShiftPhase
-from ...quantum_info import DensityMatrix, Statevector
+from ...quantum_info import DensityMatrix, Statevector, populations_by_qubit
 from ..pulse_backend import PulseBackend
 
 _FIXED = ("RK4", "jax_RK4")
@@ -88,9 +88,15 @@ class B200PulseBackend(PulseBackend):
     """PulseBackend whose ``solve`` runs on a B200 through libcasq_b200.so (no CPU fallback)."""
 
     def __init__(self, hamiltonian: HamiltonianModel, control: ControlModel, seed: Optional[int] = None, device: int = 0,
-                 noise=None):
+                 noise=None, forward_subsystem_dims: bool = False):
+        """``forward_subsystem_dims``: casq builds its DynamicsBackend WITHOUT subsystem_dims
+        (src/casq/backends/qiskit/qiskit_pulse_backend.py:184-188), so upstream treats a multi-qubit model as ONE subsystem
+        of dimension prod(dims) and ``solve`` folds every level >= 1 into "1" (SURVEY section 5 quirk 2).  False (default)
+        keeps that behaviour bit for bit; True forwards the dimensions: populations / counts are per measured qubit
+        (bit-strings, levels >= 1 of each qubit clipped to "1") and ``Solution.qubits`` lists the measured qubits."""
         self._device = int(device)
         self.noise = noise
+        self.forward_subsystem_dims = bool(forward_subsystem_dims)
         super().__init__(hamiltonian=hamiltonian, control=control, seed=seed)
         if noise is not None:
             self._native_backend.set_dissipators(noise.lindblad_operators(self.hamiltonian.qubit_dims))
@@ -246,6 +252,16 @@ class B200PulseBackend(PulseBackend):
             params_device = engine.pack_params(slot_params, device=torch.device("cuda", self._device))
         return engine.propagators_expm(self._native_backend, slots, params_device, (0.0, float(t_final) * self.control.dt), max_dt)
 
+    def gate_fidelities_batch(self, slots: Sequence[tuple], slot_params: Sequence[dict], t_final: int, max_dt: float, target,
+                              levels: int = 2, virtual_z: bool = False, params_device: Optional[torch.Tensor] = None):
+        """Average gate fidelity, process fidelity and leakage of every pulse point against ``target`` (a unitary on the
+        computational subspace), from the batched propagators in the model's rotating frame (casq_b200.fidelity)."""
+        from ...fidelity import gate_fidelities
+
+        U = self.solve_propagators_batch(slots, slot_params, t_final, max_dt, params_device)
+        qd = self.hamiltonian.qubit_dims
+        return gate_fidelities(U, target, [int(qd[q]) for q in sorted(qd)], levels, virtual_z)
+
     def solve_lindblad_batch(self, slots: Sequence[tuple], slot_params: Sequence[dict], t_final: int, max_dt: float,
                              initial_state=None, steps: Optional[int] = None, want_states: bool = False,
                              params_device: Optional[torch.Tensor] = None):
@@ -342,6 +358,9 @@ class B200PulseBackend(PulseBackend):
             run_options = {"method": method.value}
         sched, t_acq, measured = self._circuit_to_schedule(circuit)
         slots, params = self._slots_from_schedule(sched)
+        y0 = None if initial_state is None else np.asarray(getattr(initial_state, "data", initial_state))
+        if isinstance(initial_state, DensityMatrix) or (y0 is not None and y0.ndim == 2):
+            return self._solve_density_matrix(circuit.name, slots, params, t_acq, method.value, y0, shots, steps, run_options, measured)
         batch = self.solve_slots_batch(slots, params, t_acq, method.value, initial_state, steps, run_options)
         if batch.status is not None and int(batch.status[0].item()) != 0:
             raise CasqError(f"Adaptive solve failed for this circuit (status {int(batch.status[0].item())}).")
@@ -349,22 +368,66 @@ class B200PulseBackend(PulseBackend):
         probs = batch.probabilities[0].cpu().numpy()
         return self._to_solution(circuit.name, batch.times, states, probs, shots, measured)
 
-    def _to_solution(self, name, times, states, probs, shots, measured) -> "PulseBackend.Solution":
-        """get_experiment_result + convert_to_solution (helpers.py:58-230) for one experiment."""
+    def _solve_density_matrix(self, name, slots, params, t_acq, method, rho0, shots, steps, run_options, measured):
+        """The DensityMatrix branch of get_experiment_result (src/casq/backends/qiskit/helpers.py:110-121): the Lindblad
+        kernels integrate rho (with the backend's NoiseModel, or without dissipators), then per time point
+        rho <- V^+ (e^{tF} rho e^{-tF}) V and the trace is normalised."""
+        if method not in _FIXED:
+            raise CasqError("A DensityMatrix initial state is integrated by the fixed-step Lindblad path: use "
+                            "ODESolverMethod.QISKIT_DYNAMICS_RK4 with run_options['max_dt'].")
+        options = dict(run_options or {})
+        if "max_dt" not in options:
+            raise CasqError(f"Method '{method}' is a fixed-step solver and needs run_options['max_dt'].")
+        d = self.dim
+        if rho0.shape != (d, d):
+            raise CasqError(f"DensityMatrix initial state must be [{d},{d}], got {rho0.shape}.")
+        model = self._native_backend
+        t_span = (0.0, float(t_acq) * self.control.dt)
+        t_eval = None if steps is None else np.linspace(t_span[0], t_span[1], int(steps))
+        pdev = engine.pack_params(params, device=torch.device("cuda", self._device))
+        rho, _ = engine.solve_lindblad_rk4(model, slots, pdev, rho0, t_span, options["max_dt"], t_eval, want_rho=True, want_pops=False)
+        times = np.asarray(t_span) if t_eval is None else t_eval
+        rho = rho[0].cpu().numpy()
+        V, e = model.dressed_states, model.frame_evals  # the Lindblad path runs in a diagonal frame: frame basis = identity
+        states, probs = [], []
+        for k, t in enumerate(times):
+            ph = np.exp(-1j * e * t)
+            lab = ph[:, None] * rho[k] * ph.conj()[None, :]
+            r = V.conj().T @ lab @ V
+            r = r / np.trace(r).real
+            states.append(r)
+            probs.append(np.real(np.diag(r)))
+        return self._to_solution(name, times, np.array(states), np.array(probs), shots, measured, density=True)
+
+    def _to_solution(self, name, times, states, probs, shots, measured, density: bool = False) -> "PulseBackend.Solution":
+        """get_experiment_result + convert_to_solution (helpers.py:58-230) for one experiment.
+
+        Populations: helpers.py:129-134 (levels > 1 clipped to "1"); samples / counts: _sample_probability_dict and
+        _get_counts_from_samples with the experiment seed (:137-141); IQ: _get_iq_data (:143-159) -- per measured
+        subsystem a multinomial split of the shots over its levels, then PER LEVEL the I and the Q normal draws
+        ([UPSTREAM] qiskit-dynamics 0.4.1 appends rng.normal for I and for Q inside the same level loop), centres on the
+        unit circle at angle 2 pi level / dim, width 0.2, scaled by 2."""
         d = self.dim
         rng = np.random.default_rng(self._seed)
         seed = int(rng.integers(low=0, high=9223372036854775807))
-        theta = 2 * np.pi / d
-        centers = np.array([[np.cos(i * theta), np.sin(i * theta)] for i in range(d)])
+        qdims = self.hamiltonian.qubit_dims
+        labels = sorted(qdims)
+        if self.forward_subsystem_dims and len(labels) > 1:
+            dims = [int(qdims[q]) for q in labels]
+            missing = [q for q in measured if q not in labels]
+            if missing:
+                raise CasqError(f"Measured qubit(s) {missing} are not in the Hamiltonian model {labels}.")
+            meas_idx = [labels.index(q) for q in measured]
+            qubits = list(measured)
+        else:  # casq's behaviour: one subsystem of dimension prod(dims), reported as qubit 0
+            dims, meas_idx, qubits = [d], [0], [0]
         out_states, pops_l, samples_l, counts_l, iq_l, avg_l = [], [], [], [], [], []
+        State = DensityMatrix if density else Statevector
+        pgrid = None
         for t in range(len(times)):
-            out_states.append(Statevector(states[t], dims=(d,)))
+            out_states.append(State(states[t], dims=tuple(dims)))
             p = np.clip(probs[t], 0.0, None)
-            pop = {}
-            if p[0] > 0:
-                pop["0"] = float(p[0])
-            if p[1:].sum() > 0:
-                pop["1"] = float(p[1:].sum())
+            pop = {k: v for k, v in populations_by_qubit(p, dims, meas_idx).items() if v > 0}
             pops_l.append(pop)
             keys = list(pop.keys())
             pv = np.array([pop[k] for k in keys])
@@ -372,16 +435,29 @@ class B200PulseBackend(PulseBackend):
             samples_l.append(smp.tolist())
             vals, cnts = np.unique(smp, return_counts=True)
             counts_l.append({str(v): int(c) for v, c in zip(vals, cnts)})
-            # IQ cloud: multinomial over levels, Gaussian blobs of width 0.2 around the level centres
             rng_iq = np.random.default_rng(seed)
-            n_lvl = rng_iq.multinomial(shots, p / p.sum())
-            pts_i = np.concatenate([rng_iq.normal(centers[i, 0], 0.2, n) for i, n in enumerate(n_lvl)])
-            pts_q = np.concatenate([rng_iq.normal(centers[i, 1], 0.2, n) for i, n in enumerate(n_lvl)])
-            iq = 2 * np.stack([pts_i, pts_q], axis=1)
-            iq_l.append([(float(a), float(b)) for a, b in iq])
-            avg = iq.mean(axis=0)
-            avg_l.append((float(avg[0]), float(avg[1])))
+            pgrid = p.reshape([dims[k] for k in reversed(range(len(dims)))])  # axis 0 = last subsystem
+            full_i, full_q = [], []
+            for sub in meas_idx:
+                axis = len(dims) - 1 - sub
+                psub = pgrid.sum(axis=tuple(a for a in range(len(dims)) if a != axis))
+                theta = 2 * np.pi / dims[sub]
+                n_lvl = rng_iq.multinomial(shots, psub / psub.sum())
+                sub_i, sub_q = [], []
+                for lvl, n in enumerate(n_lvl):
+                    sub_i.append(rng_iq.normal(np.cos(lvl * theta), 0.2, n))
+                    sub_q.append(rng_iq.normal(np.sin(lvl * theta), 0.2, n))
+                full_i.append(np.concatenate(sub_i))
+                full_q.append(np.concatenate(sub_q))
+            iq = 2 * np.stack([np.array(full_i).T, np.array(full_q).T], axis=-1)  # [shots, slots, 2]
+            if len(meas_idx) == 1:
+                iq_l.append([(float(a), float(b)) for a, b in iq[:, 0, :]])
+                avg = iq[:, 0, :].mean(axis=0)
+                avg_l.append((float(avg[0]), float(avg[1])))
+            else:
+                iq_l.append(iq.tolist())
+                avg_l.append(iq.mean(axis=0).tolist())
         return PulseBackend.Solution(
-            circuit_name=name, qubits=[0], times=np.asarray(times), samples=samples_l, counts=counts_l,
+            circuit_name=name, qubits=qubits, times=np.asarray(times), samples=samples_l, counts=counts_l,
             populations=pops_l, states=out_states, iq_data=iq_l, avg_iq_data=avg_l, shots=shots, seed=seed,
             is_success=True, timestamp=datetime.timestamp(datetime.now()))

@@ -11,7 +11,7 @@ from casq_b200._native import NativeModel
 from casq_b200.backends import BackendLibrary, PulseBackend, build
 from casq_b200.gates import CrossResonancePulseGate, DragPulseGate, GaussianSquarePulseGate, PulseCircuit
 from casq_b200.models import ControlModel, TransmonModel
-from casq_b200.pulse import DriveChannel, ShiftFrequency, ShiftPhase
+from casq_b200.pulse import DriveChannel, Play, Schedule, ShiftFrequency, ShiftPhase
 
 pytestmark = pytest.mark.gpu
 DT = O.MANILA_DT
@@ -124,9 +124,11 @@ def test_solve_batch_detuning_reduces_to_solve_with_shift_frequency():
                                 detuning=np.array([2.5e7, -1e7]), angle=np.array([0.4, 0.0]))
     circuit = PulseCircuit(1, 1)
     circuit.pulse_gate(gate, params, 0)
-    sched = circuit.calibrations[gate.name][((0,), ())]
+    sched = Schedule(name="detuned")  # shift instructions first, then the gate's Play (same start sample: insertion order)
     sched.insert(0, ShiftFrequency(2.5e7, DriveChannel(0)))
     sched.insert(0, ShiftPhase(0.4, DriveChannel(0)))
+    sched.insert(0, Play(gate.pulse(params), DriveChannel(0)))
+    circuit.add_calibration(gate.name, [0], sched, [])
     circuit.measure(0, 0)
     sol = backend.solve(circuit, RK4, run_options=dict(opts))
     assert np.abs(sol.states[-1].data - batch.states[0, -1].cpu().numpy()).max() < 1e-13
@@ -188,3 +190,84 @@ def test_cross_resonance_gate_on_control_channel_two_transmons():
     assert np.abs(one.states[-1].data - want[2, -1]).max() < 1e-9
     with pytest.raises(Exception):
         circuit.pulse_gate(gate, {"sigma": 4.0, "width": 1.0}, 0)  # a two-qubit gate needs (control, target)
+
+
+def test_solve_with_density_matrix_initial_state_matches_oracle():
+    """The DensityMatrix branch of casq's result function (src/casq/backends/qiskit/helpers.py:110-121): solve() routes a
+    DensityMatrix initial state to the Lindblad kernels (with and without a NoiseModel) and returns DensityMatrix states."""
+    from casq_b200.models import NoiseModel
+    from casq_b200.quantum_info import DensityMatrix
+
+    rng = np.random.default_rng(12)
+    x = rng.normal(size=(3, 2)) + 1j * rng.normal(size=(3, 2))
+    rho0 = x @ x.conj().T
+    rho0 /= np.trace(rho0).real
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    gate = DragPulseGate(duration=24, amplitude=0.6)
+    circuit = PulseCircuit.from_pulse_gate(gate, {"sigma": 5.0, "beta": 1.2})
+    for noise in (None, NoiseModel({0: NoiseModel.QubitNoise(t1=40e-9, t2=30e-9)})):
+        h = TransmonModel.manila(extracted_qubits=[0])
+        c = ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+        backend = build(BackendLibrary.B200, h, c, seed=5) if noise is None else \\
+            type(build(BackendLibrary.B200, h, c, seed=5))(h, c, seed=5, noise=noise)
+        Ls = np.zeros((1, 3, 3), dtype=complex) if noise is None else noise.lindblad_operators({0: 3})
+        om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st, dissipators=Ls)
+        sol = backend.solve(circuit, RK4, initial_state=DensityMatrix(rho0), steps=4, run_options={"max_dt": DT / 40})
+        p = dict(amp=0.6, angle=0.0, sigma=5.0, beta=1.2)
+        samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", 24)], [p])
+        te = np.linspace(0, 24 * DT, 4)
+        _, rho = O.lindblad_rk4_solve(om, samples, rho0, (0.0, 24 * DT), DT / 40, te)
+        want = O.postprocess_density_matrices(om, te, rho, normalize=True)[0]
+        assert len(sol.states) == 4 and isinstance(sol.states[-1], DensityMatrix)
+        got = np.array([s.data for s in sol.states])
+        assert np.abs(got - want).max() < 1e-9
+        pr = np.real(np.diag(want[-1]))
+        assert sol.populations[-1]["0"] == pytest.approx(pr[0], abs=1e-9) and sol.populations[-1]["1"] == pytest.approx(pr[1:].sum(), abs=1e-9)
+        assert sum(sol.counts[-1].values()) == 1024
+    with pytest.raises(Exception, match="fixed-step"):
+        backend.solve(circuit, PulseBackend.ODESolverMethod.QISKIT_DYNAMICS_JAX_ODEINT, initial_state=DensityMatrix(rho0))
+
+
+def test_forwarded_subsystem_dims_give_per_qubit_populations():
+    """casq does not forward subsystem_dims (qiskit_pulse_backend.py:184-188): a two-transmon solve folds everything into one
+    pseudo-qubit.  forward_subsystem_dims=True reports the measured qubits; the default keeps casq's behaviour."""
+    h = TransmonModel.manila(extracted_qubits=[0, 1])
+    c = ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+    plain = build(BackendLibrary.B200, h, c, seed=9)
+    fwd = type(plain)(h, c, seed=9, forward_subsystem_dims=True)
+    gate = DragPulseGate(duration=32, amplitude=0.35)
+    circuit = PulseCircuit(2, 2)
+    circuit.pulse_gate(gate, {"sigma": 8.0, "beta": 0.5}, 1)
+    circuit.measure(0, 0)
+    circuit.measure(1, 1)
+    a = plain.solve(circuit, RK4, run_options={"max_dt": DT / 40})
+    b = fwd.solve(circuit, RK4, run_options={"max_dt": DT / 40})
+    assert np.abs(a.states[-1].data - b.states[-1].data).max() == 0.0
+    probs = np.abs(a.states[-1].data) ** 2
+    assert a.qubits == [0] and set(a.populations[-1]) <= {"0", "1"}
+    assert a.populations[-1]["0"] == pytest.approx(probs[0]) and a.populations[-1]["1"] == pytest.approx(probs[1:].sum())
+    assert b.qubits == [0, 1] and b.states[-1].dims() == (3, 3)
+    want = O.populations_dict(probs, subsystem_dims=[3, 3], measured=(0, 1))
+    assert {k: v for k, v in b.populations[-1].items()} == pytest.approx({k: v for k, v in want.items() if v > 0})
+    assert b.populations[-1]["10"] > 0.5  # the drive is on qubit 1 (left bit)
+    assert sum(b.counts[-1].values()) == 1024 and np.array(b.iq_data[-1]).shape == (1024, 2, 2)
+
+
+def test_gate_fidelities_from_propagators_match_oracle():
+    """X-gate fidelity of a DRAG amplitude sweep from the batched propagators: the device numbers equal the same formula
+    applied to the oracle's exponential-midpoint propagators, and the sweep has a high-fidelity point near the pi pulse."""
+    from casq_b200.fidelity import gate_fidelities
+
+    backend = _backend()
+    st, ops, ch, _ = O.parse_hamiltonian_dict(O.MANILA, [0])
+    om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st)
+    B, dur = 24, 64
+    amp = np.linspace(0.3, 0.6, B)
+    p = dict(amp=amp, angle=0.0, sigma=16.0, beta=0.6)
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    slots = [("drag", ch.index("d0"), 0, dur)]
+    fa, fp, leak = backend.gate_fidelities_batch(slots, [p], dur, DT / 40, X, virtual_z=True)
+    Uo = O.expm_midpoint_propagators(om, O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p]), (0.0, dur * DT), DT / 40)
+    fa_o, fp_o, leak_o = gate_fidelities(torch.as_tensor(Uo), X, [3], virtual_z=True)
+    assert float((fa.cpu() - fa_o).abs().max()) < 1e-9 and float((leak.cpu() - leak_o).abs().max()) < 1e-9
+    assert float(fa.max()) > 0.99 and float(fa.min()) < 0.9 and float(leak.max()) < 0.05

@@ -188,3 +188,37 @@ def test_measurement_script_problems_equal_the_oracle_definitions():
     for f in pathlib.Path(P.__file__).parent.glob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f.name
+
+
+def test_gate_fidelity_definitions():
+    """casq_b200.fidelity on CPU tensors: closed-form cases (identity, global phase, leakage, virtual Z, two qubits)."""
+    import torch
+    from casq_b200.fidelity import computational_indices, gate_fidelities
+
+    assert computational_indices([3, 3]).tolist() == [0, 1, 3, 4] and computational_indices([3]).tolist() == [0, 1]
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    U = np.zeros((4, 3, 3), dtype=complex)
+    U[0, :2, :2] = X
+    U[0, 2, 2] = 1                                  # perfect X
+    U[1, :2, :2] = np.exp(0.7j) * X
+    U[1, 2, 2] = 1                                  # global phase: same fidelity
+    c = np.cos(0.3)
+    U[2] = np.array([[0, 1, 0], [c, 0, -np.sin(0.3)], [np.sin(0.3), 0, c]])  # |0> leaks into |2>
+    U[3, :2, :2] = X @ np.diag([1, np.exp(1.1j)])
+    U[3, 2, 2] = 1                                  # X up to a Z rotation
+    fa, fp, leak = gate_fidelities(torch.as_tensor(U), X, [3])
+    assert fa[:2].tolist() == pytest.approx([1, 1]) and fp[:2].tolist() == pytest.approx([1, 1]) and leak[:2].tolist() == pytest.approx([0, 0])
+    # M = diag(c, 1): F_avg = (c^2 + 1 + (1 + c)^2) / 6, leakage = (1 - c^2) / 2
+    assert float(fa[2]) == pytest.approx((c * c + 1 + (1 + c) ** 2) / 6) and float(leak[2]) == pytest.approx((1 - c * c) / 2)
+    assert float(fp[3]) == pytest.approx(abs(1 + np.exp(1.1j)) ** 2 / 4)
+    fz, _, _ = gate_fidelities(torch.as_tensor(U), X, [3], virtual_z=True)
+    assert float(fz[3]) == pytest.approx(1.0) and float(fz[0]) == pytest.approx(1.0)
+    # two qutrits: CNOT embedded in 9 x 9 is found on the 4 computational states
+    cnot = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=complex)  # control = subsystem 0
+    U9 = np.eye(9, dtype=complex)
+    idx = computational_indices([3, 3])
+    U9[np.ix_(idx, idx)] = cnot
+    fa9, fp9, l9 = gate_fidelities(torch.as_tensor(U9[None]), cnot, [3, 3])
+    assert float(fa9[0]) == pytest.approx(1.0) and float(l9[0]) == pytest.approx(0.0)
+    with pytest.raises(CasqError):
+        gate_fidelities(torch.as_tensor(U9[None]), X, [3, 3])
