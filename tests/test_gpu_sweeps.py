@@ -208,8 +208,9 @@ def test_solve_with_density_matrix_initial_state_matches_oracle():
     for noise in (None, NoiseModel({0: NoiseModel.QubitNoise(t1=40e-9, t2=30e-9)})):
         h = TransmonModel.manila(extracted_qubits=[0])
         c = ControlModel(dt=DT, channel_carrier_freqs=O.MANILA_CARRIERS)
-        backend = build(BackendLibrary.B200, h, c, seed=5) if noise is None else \\
-            type(build(BackendLibrary.B200, h, c, seed=5))(h, c, seed=5, noise=noise)
+        backend = build(BackendLibrary.B200, h, c, seed=5)
+        if noise is not None:
+            backend = type(backend)(h, c, seed=5, noise=noise)
         Ls = np.zeros((1, 3, 3), dtype=complex) if noise is None else noise.lindblad_operators({0: 3})
         om = O.OracleModel(st, ops, ch, O.MANILA_CARRIERS, DT, rotating_frame=st, dissipators=Ls)
         sol = backend.solve(circuit, RK4, initial_state=DensityMatrix(rho0), steps=4, run_options={"max_dt": DT / 40})
