@@ -12,6 +12,7 @@
 // partial pivoting, then s squarings.  d < 16 here, so this is CUDA-core complex arithmetic;
 // a split-complex tensor-core GEMM only pays for d >= 16 (north_star) and is not built.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -711,7 +712,9 @@ extern "C" int casq_propagators_expm(casq_model* m, int n_slots, const casq_puls
       propagator_expm_block_kernel<TS_, false><<<(unsigned)Bc, PB_THREADS, smem_b, st>>>(a);                                               \
     }                                                                                                                                      \
   }
-      if (d % 3 == 0) PROP_BLOCK_LAUNCH(3)
+      // products on the FP64 tensor pipe (DMMA split-complex GEMM) unless CASQ_PROP_NO_MMA asks for the CUDA-core tiles
+      if (!getenv("CASQ_PROP_NO_MMA")) PROP_BLOCK_LAUNCH(0)
+      else if (d % 3 == 0) PROP_BLOCK_LAUNCH(3)
       else if (d % 2 == 0) PROP_BLOCK_LAUNCH(2)
       else PROP_BLOCK_LAUNCH(1)
 #undef PROP_BLOCK_LAUNCH

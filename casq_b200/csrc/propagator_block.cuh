@@ -17,19 +17,77 @@
 #ifndef PB_TILE_ROWS
 #define PB_TILE_ROWS(TS) (TS)  // square tiles: 1 x TS tiles put 3x the threads to work at dim 27 but ran 11 % slower (operand traffic)
 #endif
+// ---- tensor-core product: split-complex GEMM on the FP64 tensor pipe (DMMA.8x8x4 = mma.sync m8n8k4 f64) -------------------
+// north_star (3): "run on tensor cores via split-complex GEMM only where d >= 16 makes it a real dense contraction".
+// C = X Y with X = Xr + i Xi, Y = Yr + i Yi as four real 8x8x4 MMAs per k-step: Cr += Xr Yr, Cr += (-Xi) Yi, Ci += Xr Yi,
+// Ci += Xi Yr, accumulators in registers (fp64: same precision as the FMA path, results differ by summation order only).
+// A warp owns an 8 x 16 strip of C (two 8 x 8 tiles sharing the X fragment); fragments are read straight from the
+// interleaved complex matrices: one 16 B load gives the (re, im) pair of an operand element, so a k-step of 4 costs 3
+// loads per lane for 8 MMAs = 512 complex FMAs per warp (the register-tiled CUDA-core product loads 6 operands per 9).
+// m8n8k4 fragment layout: a = A[lane / 4][lane % 4], b = B[lane % 4][lane / 4], c0/c1 = C[lane / 4][2 (lane % 4) + 0/1].
+__device__ __forceinline__ void pb_dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void bmatmul_mma(int d, int tid, double2* C, const double2* X, const double2* Y) {
+  const int lane = tid & 31, warp = tid >> 5, gr = lane >> 2, gk = lane & 3;
+  const int nt = (d + 7) >> 3, npair = (nt + 1) >> 1;
+  const double2 z = make_double2(0.0, 0.0);
+  for (int job = warp; job < nt * npair; job += PB_THREADS / 32) {
+    const int ti = job / npair, tp = job - ti * npair;
+    const int r = ti * 8 + gr, ca = tp * 16 + gr, cb = ca + 8;
+    const bool rok = r < d, caok = ca < d, cbok = cb < d;
+    double cr0[2] = {0.0, 0.0}, ci0[2] = {0.0, 0.0}, cr1[2] = {0.0, 0.0}, ci1[2] = {0.0, 0.0};
+    const double2* xp = X + r * d + gk;
+    const double2* yp = Y + gk * d + ca;
+#pragma unroll 2
+    for (int k0 = 0; k0 < d; k0 += 4) {
+      const bool kok = k0 + gk < d;
+      const double2 a = (rok && kok) ? xp[k0] : z;
+      const double2 b0 = (kok && caok) ? yp[k0 * d] : z;
+      const double2 b1 = (kok && cbok) ? yp[k0 * d + 8] : z;
+      const double nai = -a.y;
+      pb_dmma(cr0, a.x, b0.x);
+      pb_dmma(ci0, a.x, b0.y);
+      pb_dmma(cr1, a.x, b1.x);
+      pb_dmma(ci1, a.x, b1.y);
+      pb_dmma(cr0, nai, b0.y);
+      pb_dmma(ci0, a.y, b0.x);
+      pb_dmma(cr1, nai, b1.y);
+      pb_dmma(ci1, a.y, b1.x);
+    }
+    if (rok) {
+      const int c0 = tp * 16 + 2 * gk;
+      double2* o = C + r * d + c0;
+      if (c0 < d) o[0] = make_double2(cr0[0], ci0[0]);
+      if (c0 + 1 < d) o[1] = make_double2(cr0[1], ci0[1]);
+      if (c0 + 8 < d) o[8] = make_double2(cr1[0], ci1[0]);
+      if (c0 + 9 < d) o[9] = make_double2(cr1[1], ci1[1]);
+    }
+  }
+  __syncthreads();
+}
+
+// TS = 0 selects the tensor-core product above; TS >= 1 the register-tiled CUDA-core product (kept for A/B runs:
+// CASQ_PROP_NO_MMA=1).
 template <int TS>
 __device__ __forceinline__ void bmatmul(int d, int tid, double2* C, const double2* X, const double2* Y) {
-  constexpr int TR = PB_TILE_ROWS(TS);
-  const int ntr = d / TR, ntc = d / TS, ntiles = ntr * ntc;
+  if constexpr (TS == 0) {
+    bmatmul_mma(d, tid, C, X, Y);
+    return;
+  }
+  constexpr int TR = PB_TILE_ROWS(TS == 0 ? 1 : TS);
+  const int ntr = d / TR, ntc = d / (TS == 0 ? 1 : TS), ntiles = ntr * ntc;
   for (int tile = tid; tile < ntiles; tile += PB_THREADS) {
     const int ti = tile / ntc, r0 = ti * TR, c0 = (tile - ti * ntc) * TS;
-    double2 acc[TR][TS];
+    constexpr int TC = TS == 0 ? 1 : TS;
+    double2 acc[TR][TC];
 #pragma unroll
     for (int i = 0; i < TR; i++)
 #pragma unroll
       for (int j = 0; j < TS; j++) acc[i][j] = make_double2(0.0, 0.0);
     for (int k = 0; k < d; k++) {
-      double2 x[TR], y[TS];
+      double2 x[TR], y[TC];
 #pragma unroll
       for (int i = 0; i < TR; i++) x[i] = X[(r0 + i) * d + k];
 #pragma unroll
