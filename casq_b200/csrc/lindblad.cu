@@ -37,6 +37,11 @@ __global__ void sv_general_table_kernel(const double* __restrict__ times, long l
 int casq_prepare_slots(const casq_model* m, int n_slots, const casq_pulse_slot* slots, DevSlots* ds, int* active,
                        int* n_active, int* n_total);
 
+// RK4 stages that run the TMA-staged kernel by default (bit 0 = stage 1); see lindblad_run_chain
+#ifndef LC_DEFAULT_TMA_STAGES
+#define LC_DEFAULT_TMA_STAGES 15
+#endif
+
 namespace {
 struct Atom {
   int row, col, sig;
@@ -269,7 +274,7 @@ static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector
     for (int c = 0; c < d; c++) {
       cplx g = adiag[r] + std::conj(adiag[c]);
       for (const auto& l : diagL) g += l[r] * std::conj(l[c]);
-      P.G[(size_t)r * ld + c + (c / LC_T) * (LC_TS - LC_T)] = g;
+      P.G[((size_t)(r / LC_T) * (d / LC_T) + c / LC_T) * (LC_T * LC_TS) + (r % LC_T) * LC_TS + c % LC_T] = g;  // tile-major (lb_idx)
     }
   P.ok = true;
   return P;
@@ -281,7 +286,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
                               int n_total, int64_t B, const double* params_dev, const double* rho0_dev, int rho0_batched,
                               double t0, double t1, double max_dt, int T, const double* t_eval, double* out_rho_dev,
                               double* out_pops_dev, cudaStream_t st) {
-  const int d = m->d, ld = (d / LC_T) * LC_TS;  // 27-column tiles padded to 32 (lb_col)
+  const int d = m->d, ld = (d / LC_T) * LC_TS;  // tile-major storage, 27-column tiles padded to 32 (lb_idx): d * ld elements per matrix
   const int tw = LC_T, tpad = LC_TS - LC_T;
   int rc;
   TimeGrid g;
@@ -355,7 +360,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   if ((rc = m->work1.ensure(blob.size()))) return rc;
   // Gathers are unconditional (invalid columns carry a zero coefficient): the buffers are zero-filled once per solve, row
   // padding included, with slack in front of the first and behind the last matrix.
-  const size_t slack = 64;  // elements
+  const size_t slack = 2 * (size_t)LC_T * LC_TS;  // elements (two tiles): staged windows may run past the last tile
   const size_t w2_bytes = (4 * (size_t)B * n_pad + 2 * slack) * 16;
   if ((rc = m->work2.ensure(w2_bytes))) return rc;
   CASQ_CUDA(cudaMemsetAsync(m->work2.p, 0, w2_bytes, st));
@@ -398,16 +403,26 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   c.atom_val = (const double2*)(dev + o_av);
   c.atom_code = (const int*)(dev + o_ac);
   const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
-  const size_t smem_stage = lindblad_chain_smem(cp.NC);
   const bool low_only = (cp.drv_mask & 6u) == 0;  // only site 0 of the low three is driven (cfg 4): leaner in-tile code
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_chain_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
-  void (*stage_fn)(const LcArgs, int, const LbStage) = nullptr;
-#define LC_PICK(NQ_)                                                                                   \
-  if (cp.nq == NQ_) stage_fn = low_only ? lindblad_chain_stage_kernel<NQ_, 1> : lindblad_chain_stage_kernel<NQ_, 7>;
+  // Two implementations of the same stage (lindblad_chain.cuh): operands through the LSU (LDG) or staged by bulk asynchronous
+  // copies (TMA).  CASQ_LB_TMA_STAGES is a bit mask of the RK4 stages (bit 0 = stage 1) that use the TMA kernel.
+  typedef void (*StageFn)(const LcArgs, int, const LbStage);
+  StageFn fn_ldg = nullptr, fn_tma = nullptr;
+#define LC_PICK(NQ_)                                                                                             \
+  if (cp.nq == NQ_) {                                                                                            \
+    fn_tma = low_only ? lindblad_chain_tma_kernel<NQ_, 1> : lindblad_chain_tma_kernel<NQ_, 7>;                   \
+    fn_ldg = low_only ? lindblad_chain_stage_kernel<NQ_, 1> : lindblad_chain_stage_kernel<NQ_, 7>;               \
+  }
   LC_PICK(3) LC_PICK(4) LC_PICK(5) LC_PICK(6)
 #undef LC_PICK
-  if (!stage_fn) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "chain kernel: %d sites", cp.nq);
-  CASQ_CUDA(cudaFuncSetAttribute(stage_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stage));
+  if (!fn_ldg) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "chain kernel: %d sites", cp.nq);
+  const size_t smem_tma = lindblad_chain_tma_smem(cp.NC), smem_ldg = lindblad_chain_smem(cp.NC);
+  CASQ_CUDA(cudaFuncSetAttribute(fn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+  CASQ_CUDA(cudaFuncSetAttribute(fn_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg));
+  int tma_stages = LC_DEFAULT_TMA_STAGES;
+  if (const char* e = getenv("CASQ_LB_TMA_STAGES")) tma_stages = atoi(e) & 15;
+  if (getenv("CASQ_LB_NO_TMA")) tma_stages = 0;
 
   struct Part {
     LbArgs a;
@@ -491,7 +506,10 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
           sg.out = stage == 4 ? P.bufs[0] : P.bufs[stage];
           sg.stage = stage;
           sg.h = h_piece;
-          stage_fn<<<grid, 32 * LC_WARPS, smem_stage, P.st>>>(P.c, set, sg);
+          if ((tma_stages >> (stage - 1)) & 1)
+            fn_tma<<<grid, 32 * LC_WARPS, smem_tma, P.st>>>(P.c, set, sg);
+          else
+            fn_ldg<<<grid, 32 * LC_WARPS, smem_ldg, P.st>>>(P.c, set, sg);
         }
       }
       pos += 2;

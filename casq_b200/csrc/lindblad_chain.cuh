@@ -169,8 +169,9 @@ struct LcList {  // gather terms of one warp for one segment: nine rows each, wa
   int pad;
 };
 
-// one-sided gather terms of the rows (R, x_2 = g): everything of A that leaves the nine-row group except J_12
-template <int NQ, int LD>
+// one-sided gather terms of the rows (R, x_2 = g): everything of A that leaves the nine-row group except J_12.
+// Offsets in elements of the tile-major storage: RS = row stride inside a tile, TROW = stride between tile rows.
+template <int NQ, int RS, int TROW>
 __device__ __forceinline__ void lc_build_one_sided(LcList* L, int R, int g, unsigned drv_mask) {
   const int jbase = 4 * NQ;
   int n = 0;
@@ -181,25 +182,25 @@ __device__ __forceinline__ void lc_build_one_sided(LcList* L, int R, int g, unsi
     rr /= 3;
   }
   if ((drv_mask >> 2) & 1u) {  // X_2: source group g + 1 / g - 1 of the same tile
-    if (g <= 1) { L->off[n] = 9 * LD; L->slot[n++] = (2 * 2 + 0) * 2 + g; }
-    if (g >= 1) { L->off[n] = -9 * LD; L->slot[n++] = (2 * 2 + 1) * 2 + g - 1; }
+    if (g <= 1) { L->off[n] = 9 * RS; L->slot[n++] = (2 * 2 + 0) * 2 + g; }
+    if (g >= 1) { L->off[n] = -9 * RS; L->slot[n++] = (2 * 2 + 1) * 2 + g - 1; }
   }
   if (NQ >= 4) {  // J_23: r + 27 - 9 (x_2 >= 1, x_3 <= 1: n = x_2 - 1, m = x_3) and r - 27 + 9 (x_2 <= 1, x_3 >= 1: n = x_2, m = x_3 - 1)
     const int x3 = xd[3];
-    if (g >= 1 && x3 <= 1) { L->off[n] = 18 * LD; L->slot[n++] = jbase + ((2 * 2 + 0) * 2 + g - 1) * 2 + x3; }
-    if (g <= 1 && x3 >= 1) { L->off[n] = -18 * LD; L->slot[n++] = jbase + ((2 * 2 + 1) * 2 + g) * 2 + x3 - 1; }
+    if (g >= 1 && x3 <= 1) { L->off[n] = TROW - 9 * RS; L->slot[n++] = jbase + ((2 * 2 + 0) * 2 + g - 1) * 2 + x3; }
+    if (g <= 1 && x3 >= 1) { L->off[n] = -(TROW - 9 * RS); L->slot[n++] = jbase + ((2 * 2 + 1) * 2 + g) * 2 + x3 - 1; }
   }
-  int pw = 27;
-  for (int q = 3; q < NQ; q++, pw *= 3) {
+  int tw = 1;  // 3^(q - 3): shift in tile rows
+  for (int q = 3; q < NQ; q++, tw *= 3) {
     const int xq = xd[q];
     if ((drv_mask >> q) & 1u) {
-      if (xq <= 1) { L->off[n] = pw * LD; L->slot[n++] = (q * 2 + 0) * 2 + xq; }
-      if (xq >= 1) { L->off[n] = -pw * LD; L->slot[n++] = (q * 2 + 1) * 2 + xq - 1; }
+      if (xq <= 1) { L->off[n] = tw * TROW; L->slot[n++] = (q * 2 + 0) * 2 + xq; }
+      if (xq >= 1) { L->off[n] = -tw * TROW; L->slot[n++] = (q * 2 + 1) * 2 + xq - 1; }
     }
     if (q + 1 < NQ) {
       const int xq1 = xd[q + 1];
-      if (xq >= 1 && xq1 <= 1) { L->off[n] = 2 * pw * LD; L->slot[n++] = jbase + ((q * 2 + 0) * 2 + xq - 1) * 2 + xq1; }
-      if (xq <= 1 && xq1 >= 1) { L->off[n] = -2 * pw * LD; L->slot[n++] = jbase + ((q * 2 + 1) * 2 + xq) * 2 + xq1 - 1; }
+      if (xq >= 1 && xq1 <= 1) { L->off[n] = 2 * tw * TROW; L->slot[n++] = jbase + ((q * 2 + 0) * 2 + xq - 1) * 2 + xq1; }
+      if (xq <= 1 && xq1 >= 1) { L->off[n] = -2 * tw * TROW; L->slot[n++] = jbase + ((q * 2 + 1) * 2 + xq) * 2 + xq1 - 1; }
     }
   }
   L->n = n;
@@ -211,7 +212,7 @@ static inline size_t lindblad_chain_smem(int NC) {
 
 template <int NQ, int XLOW>
 __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_stage_kernel(const LcArgs a, int set, const LbStage s) {
-  constexpr int D = lc_pow3(NQ), LD = (D / LC_T) * LC_TS;  // every 27-column tile starts on a 512 B boundary
+  constexpr int D = lc_pow3(NQ), NT = D / LC_T, LD = NT * LC_TS, RS = LC_TS, TSZ = LC_T * LC_TS, TROW = NT * TSZ;  // tile-major (lb_idx)
   extern __shared__ __align__(16) unsigned char lc_smem[];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int NCs = (a.NC + 1) & ~1;
@@ -230,8 +231,8 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
     for (int i = threadIdx.x; i < a.NC; i += 32 * LC_WARPS) ct[i] = __ldg(src + i);
   }
   if (lane == 0) {
-    if (!diag) lc_build_one_sided<NQ, LD>(lists + 0, J, g, a.drv_mask);
-    lc_build_one_sided<NQ, LD>(lists + 1, I, g, a.drv_mask);
+    if (!diag) lc_build_one_sided<NQ, RS, TROW>(lists + 0, J, g, a.drv_mask);
+    lc_build_one_sided<NQ, RS, TROW>(lists + 1, I, g, a.drv_mask);
     int n = 0;
     for (int k = 0; k < a.n2; k++) {  // two-sided terms of the sites in the tile INDEX: warp-uniform coefficient W(k, nr, nc)
       const int q = a.two_q[k];
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
       }
       const int nr = ti % 3, nc = tj % 3;
       if (nr > 1 || nc > 1) continue;
-      lists[2].off[n] = pw * (27 * LD + LC_TS);
+      lists[2].off[n] = pw * (TROW + TSZ);
       lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
     }
     lists[2].n = n;
@@ -252,19 +253,19 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
   __syncthreads();
   const long long base = b * (long long)D * LD;
   const double2* in = s.in + base;
-  const long long o0 = (long long)(LC_T * I + 9 * g) * LD + LC_TS * J + cl;   // this warp's rows of tile (I, J)
+  const long long o0 = ((long long)I * NT + J) * TSZ + 9 * g * RS + cl;   // this warp's rows of tile (I, J)
   const double2* cJ12 = ct + 4 * NQ + (1 * 2 + 0) * 4;  // J(1, dir, n, m) = cJ12[(dir*2 + n)*2 + m]
   double2 acc[9];
   // seg 0: M_JI = (A rho)[J, I] -> sT;  seg 1: M_IJ (diagonal pair: also -> sT);  seg 2: + two-sided terms of (I, J)
 #pragma unroll 1
   for (int seg = diag ? 1 : 0; seg < 3; seg++) {
-    const double2* p = seg == 0 ? in + (long long)(LC_T * J + 9 * g) * LD + LC_TS * I + cl : in + o0;
+    const double2* p = seg == 0 ? in + ((long long)J * NT + I) * TSZ + 9 * g * RS + cl : in + o0;
     if (seg < 2) {
       lc_zero9(acc);
-      lc_in_group<NQ, LD, XLOW>(acc, p, ct);
+      lc_in_group<NQ, RS, XLOW>(acc, p, ct);
       // J_12 inside the tile: s = t + 6 (x_1(t) >= 1, g <= 1: n = x_1(t) - 1, m = g);  s = t - 6 (x_1(t) <= 1, g >= 1: n = x_1(t), m = g - 1)
-      if (g <= 1) lc_apply_digit9<LD, 1, 1>(acc, p + 6 * LD, cJ12[(0 * 2 + 0) * 2 + g], cJ12[(0 * 2 + 1) * 2 + g]);
-      if (g >= 1) lc_apply_digit9<LD, 1, 0>(acc, p - 6 * LD, cJ12[(1 * 2 + 0) * 2 + g - 1], cJ12[(1 * 2 + 1) * 2 + g - 1]);
+      if (g <= 1) lc_apply_digit9<RS, 1, 1>(acc, p + 6 * RS, cJ12[(0 * 2 + 0) * 2 + g], cJ12[(0 * 2 + 1) * 2 + g]);
+      if (g >= 1) lc_apply_digit9<RS, 1, 0>(acc, p - 6 * RS, cJ12[(1 * 2 + 0) * 2 + g - 1], cJ12[(1 * 2 + 1) * 2 + g - 1]);
     } else {
       // two-sided terms of the sites inside the tile (lowering operators): rho[r + 3^q, c + 3^q] for rows and lanes whose
       // digit q is <= 1; coefficient W(k, nr = x_q(row), nc = x_q(lane)) = ct[w_base + 4k + 2 nr + nc]
@@ -276,16 +277,16 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
         const int xl = q == 0 ? cl % 3 : (q == 1 ? (cl / 3) % 3 : cl / 9);
         const bool ok = xl <= 1;
         const int xx = ok ? xl : 0;
-        if (q == 0) lc_apply_digit9<LD, 0, 0>(acc, p + (LD + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
-        if (q == 1) lc_apply_digit9<LD, 1, 0>(acc, p + 3 * (LD + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
-        if (q == 2 && g <= 1) lc_apply9<LD>(acc, p + 9 * (LD + 1), ok ? ct[wb + 2 * g + xx] : z);
+        if (q == 0) lc_apply_digit9<RS, 0, 0>(acc, p + (RS + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 1) lc_apply_digit9<RS, 1, 0>(acc, p + 3 * (RS + 1), ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 2 && g <= 1) lc_apply9<RS>(acc, p + 9 * (RS + 1), ok ? ct[wb + 2 * g + xx] : z);
       }
     }
     {
       const LcList* L = lists + seg;
       const int n = L->n;
 #pragma unroll 1
-      for (int i = 0; i < n; i++) lc_apply9<LD>(acc, p + L->off[i], ct[L->slot[i]]);
+      for (int i = 0; i < n; i++) lc_apply9<RS>(acc, p + L->off[i], ct[L->slot[i]]);
     }
     if ((seg == 0 || (seg == 1 && diag)) && active) {
 #pragma unroll
@@ -310,9 +311,9 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
       double2 y0[3], v[3], gg[3];
 #pragma unroll
       for (int u = 0; u < 3; u++) {
-        y0[u] = yp[(t0 + u) * LD];
-        v[u] = __ldg(p + (t0 + u) * LD);
-        gg[u] = greal ? make_double2(__ldg(grp + (t0 + u) * LD), 0.0) : __ldg(gp + (t0 + u) * LD);
+        y0[u] = yp[(t0 + u) * RS];
+        v[u] = __ldg(p + (t0 + u) * RS);
+        gg[u] = greal ? make_double2(__ldg(grp + (t0 + u) * RS), 0.0) : __ldg(gp + (t0 + u) * RS);
       }
 #pragma unroll
       for (int u = 0; u < 3; u++) {
@@ -324,11 +325,11 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
         if (s.stage != 4) {
           res = make_double2(fma(h, k.x, y0[u].x), fma(h, k.y, y0[u].y));
         } else {  // y <- (y1 + 2 y2 + y3 - y)/3 + h/6 k4 (v = y3 is the stage input)
-          const double2 v1 = y1p[t * LD], v2 = y2p[t * LD];
+          const double2 v1 = y1p[t * RS], v2 = y2p[t * RS];
           res = make_double2(fma(h6, k.x, t3 * (v1.x + 2.0 * v2.x + v[u].x - y0[u].x)),
                              fma(h6, k.y, t3 * (v1.y + 2.0 * v2.y + v[u].y - y0[u].y)));
         }
-        outp[t * LD] = res;
+        outp[t * RS] = res;
         if (!diag) sT[lane * LC_T + 9 * g + t] = res;
       }
     }
@@ -337,11 +338,345 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
   __syncthreads();
   // ---- mirror tile: out(J*27 + r, I*27 + lane) = conj(out(I*27 + lane, J*27 + r)) = conj(sT[r][lane]), r = 9g + t
   if (active) {
-    const long long om = base + (long long)(LC_T * J + 9 * g) * LD + LC_TS * I + lane;
+    const long long om = base + ((long long)J * NT + I) * TSZ + 9 * g * RS + lane;
 #pragma unroll
     for (int t = 0; t < 9; t++) {
       const double2 r = sT[(9 * g + t) * LC_T + lane];
-      s.out[om + (long long)t * LD] = make_double2(r.x, -r.y);
+      s.out[om + t * RS] = make_double2(r.x, -r.y);
+    }
+  }
+}
+
+// =====================================================================================================================
+// TMA-staged variant (default).  Same task decomposition and arithmetic as lindblad_chain_stage_kernel above, but every
+// nine-row group a warp consumes is brought from global memory into a per-warp shared-memory ring by bulk asynchronous
+// copies (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier: the "coalesced HBM staging of the batch" north_star asks
+// for) issued up to LC_NBUF groups ahead of their use:
+//   * the LSU no longer carries the loads: a 432 B row read with LDG.128 costs ~8 L1 cycles (2 per 128 B line within one
+//     instruction, B300_MICROARCH "rt_L1tex_wf"), the same row read back from shared memory 4;
+//   * HBM / L2 latency overlaps the FMA phases without more warps or registers (the LDG version spent 50 % of its stall
+//     samples on the load scoreboard at every occupancy from 12 to 21 warps per SM).
+// The fetch list of a warp is built in consumption order by its lane 0; lanes 0..8 issue one row copy each.
+#ifndef LC_NBUF
+#define LC_NBUF 3
+#endif
+#ifndef LC_TMA_MINBLOCKS
+#define LC_TMA_MINBLOCKS 3  // shared memory (74 kB per block) allows three blocks per SM
+#endif
+#define LC_ROWB (LC_TS * 16)       // bytes of one staged row (a tile row: 27 complex + 5 padding)
+#define LC_SLOTB (9 * LC_ROWB)     // one ring slot: nine rows = one contiguous piece of the tile-major storage
+#define LC_MAXFETCH 48
+
+struct LcFetch {
+  const char* src;   // contiguous in the tile-major storage
+  int bytes;         // multiple of 16, <= LC_SLOTB
+  int pad;
+};
+
+__device__ __forceinline__ unsigned lc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lc_mbar_init(unsigned mbar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void lc_mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LC_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LC_DONE_%=;\n"
+      "bra LC_WAIT_%=;\n"
+      "LC_DONE_%=:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void lc_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+// shared memory of a block: [tile A: (J, I) tile of the stage input, later M_JI^T / the result tile][tile B: (I, J) tile]
+// [coefficient table][gather lists][per warp: ring of LC_NBUF slots, fetch list, mbarriers]
+#define LC_TILEB (LC_T * LC_ROWB)  // one staged tile: 27 rows of 32 elements
+static inline size_t lindblad_chain_tma_smem(int NC) {
+  return 2 * (size_t)LC_TILEB + (size_t)((NC + 1) & ~1) * 16 + 3 * LC_WARPS * sizeof(LcList) + 64 +
+         LC_WARPS * ((size_t)LC_NBUF * LC_SLOTB + LC_MAXFETCH * sizeof(LcFetch) + 64);
+}
+
+// consumers of a staged slot (rows at pitch 27 elements): same arithmetic as lc_in_group / lc_apply9 / lc_apply_digit9
+template <int NQ, int XLOW>
+__device__ __forceinline__ void lc_s_in_group(double2 (&acc)[9], const double2* __restrict__ b, const double2* ct) {
+  const double2* cJ = ct + 4 * NQ;
+  double2 v[9];
+#pragma unroll
+  for (int s = 0; s < 9; s++) v[s] = b[s * LC_TS];
+#pragma unroll
+  for (int s = 0; s < 9; s++) {
+    const int x0 = s % 3, x1 = s / 3;
+    if (XLOW & 1) {
+      if (x0 >= 1) lc_cfma(acc[s - 1], ct[(0 * 2 + 0) * 2 + x0 - 1], v[s]);
+      if (x0 <= 1) lc_cfma(acc[s + 1], ct[(0 * 2 + 1) * 2 + x0], v[s]);
+    }
+    if (XLOW & 2) {
+      if (x1 >= 1) lc_cfma(acc[s - 3], ct[(1 * 2 + 0) * 2 + x1 - 1], v[s]);
+      if (x1 <= 1) lc_cfma(acc[s + 3], ct[(1 * 2 + 1) * 2 + x1], v[s]);
+    }
+    if (x0 <= 1 && x1 >= 1) lc_cfma(acc[s - 2], cJ[((0 * 2 + 0) * 2 + x0) * 2 + x1 - 1], v[s]);
+    if (x0 >= 1 && x1 <= 1) lc_cfma(acc[s + 2], cJ[((0 * 2 + 1) * 2 + x0 - 1) * 2 + x1], v[s]);
+  }
+}
+__device__ __forceinline__ void lc_s_apply9(double2 (&acc)[9], const double2* __restrict__ b, const double2 c) {
+#pragma unroll
+  for (int t = 0; t < 9; t++) lc_cfma(acc[t], c, b[t * LC_TS]);
+}
+// staged rows 0..5 feed accumulators FIRST..FIRST+5: digit x_1 of the accumulator row picks the coefficient
+template <int FIRST>
+__device__ __forceinline__ void lc_s_apply6(double2 (&acc)[9], const double2* __restrict__ b, const double2 c0, const double2 c1) {
+#pragma unroll
+  for (int t = 0; t < 6; t++) lc_cfma(acc[FIRST + t], t < 3 ? c0 : c1, b[t * LC_TS]);
+}
+// staged window row t feeds accumulator t when digit Q of t is 0 (c0) or 1 (c1)
+template <int Q>
+__device__ __forceinline__ void lc_s_apply_digit9(double2 (&acc)[9], const double2* __restrict__ b, const double2 c0, const double2 c1) {
+#pragma unroll
+  for (int t = 0; t < (Q == 0 ? 8 : 6); t++) {  // only these window rows are staged
+    const int x = Q == 0 ? t % 3 : t / 3;
+    if (x == 0) lc_cfma(acc[t], c0, b[t * LC_TS]);
+    if (x == 1) lc_cfma(acc[t], c1, b[t * LC_TS]);
+  }
+}
+
+template <int NQ, int XLOW>
+__global__ void __launch_bounds__(32 * LC_WARPS, LC_TMA_MINBLOCKS) lindblad_chain_tma_kernel(const LcArgs a, int set, const LbStage s) {
+  constexpr int D = lc_pow3(NQ), NT = D / LC_T, LD = NT * LC_TS, RS = LC_TS, TSZ = LC_T * LC_TS, TROW = NT * TSZ;  // tile-major (lb_idx)
+  extern __shared__ __align__(128) unsigned char lc_smem[];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int NCs = (a.NC + 1) & ~1;
+  double2* tileA = reinterpret_cast<double2*>(lc_smem);              // [27][32]: stage input, tile (J, I)
+  double2* sT = tileA;                                               // [27][27] once tile A has been consumed
+  double2* tileB = tileA + LC_T * LC_TS;                             // [27][32]: stage input, tile (I, J)
+  double2* ct = tileB + LC_T * LC_TS;                                // [NC]
+  LcList* lists = reinterpret_cast<LcList*>(ct + NCs) + 3 * g;       // [warp][seg]
+  unsigned long long* tbar = reinterpret_cast<unsigned long long*>(reinterpret_cast<LcList*>(ct + NCs) + 3 * LC_WARPS);  // [2] tile barriers
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(tbar) + 64 + (size_t)g * ((size_t)LC_NBUF * LC_SLOTB + LC_MAXFETCH * sizeof(LcFetch) + 64);
+  unsigned char* ring = wbase;                                              // [LC_NBUF][LC_SLOTB]
+  LcFetch* fl = reinterpret_cast<LcFetch*>(wbase + (size_t)LC_NBUF * LC_SLOTB);
+  unsigned long long* mbars = reinterpret_cast<unsigned long long*>(fl + LC_MAXFETCH);  // [LC_NBUF] + nfetch
+  int* nfetch_p = reinterpret_cast<int*>(mbars + LC_NBUF);
+  const long long task = blockIdx.x;
+  const long long b = task / a.npairs;
+  const int pr = (int)(task - b * a.npairs);
+  const int I = a.pair_ij[2 * pr], J = a.pair_ij[2 * pr + 1];
+  const bool diag = I == J;
+  const bool active = lane < LC_T;
+  const int cl = active ? lane : LC_T - 1;
+  const long long base = b * (long long)D * LD;
+  const double2* in = s.in + base;
+  const long long tI = ((long long)I * NT + J) * TSZ + 9 * g * RS;  // this warp's rows of tile (I, J), column 0
+  const long long tJ = ((long long)J * NT + I) * TSZ + 9 * g * RS;
+  const bool greal = a.Gre != nullptr;
+  if (threadIdx.x == 0) {
+    lc_mbar_init(lc_smem_u32(tbar + 0), LC_WARPS);
+    lc_mbar_init(lc_smem_u32(tbar + 1), LC_WARPS);
+  }
+  if (lane == 0) {
+    for (int i = 0; i < LC_NBUF; i++) lc_mbar_init(lc_smem_u32(mbars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (lane == 0) {
+    // the two tiles of the stage input: every warp brings its own nine rows (one contiguous 4.6 kB piece each)
+    if (!diag) {
+      lc_mbar_expect_tx(lc_smem_u32(tbar + 0), 9 * LC_ROWB);
+      lc_bulk_g2s(lc_smem_u32(tileA + 9 * g * LC_TS), in + tJ, 9 * LC_ROWB, lc_smem_u32(tbar + 0));
+    }
+    lc_mbar_expect_tx(lc_smem_u32(tbar + 1), 9 * LC_ROWB);
+    lc_bulk_g2s(lc_smem_u32(tileB + 9 * g * LC_TS), in + tI, 9 * LC_ROWB, lc_smem_u32(tbar + 1));
+    if (!diag) lc_build_one_sided<NQ, RS, TROW>(lists + 0, J, g, a.drv_mask);
+    else lists[0].n = 0;
+    lc_build_one_sided<NQ, RS, TROW>(lists + 1, I, g, a.drv_mask);
+    int n = 0;
+    for (int k = 0; k < a.n2; k++) {
+      const int q = a.two_q[k];
+      if (q <= 2) continue;
+      int pw = 1, ti = I, tj = J;
+      for (int sq = 3; sq < q; sq++) {
+        pw *= 3;
+        ti /= 3;
+        tj /= 3;
+      }
+      const int nr = ti % 3, nc = tj % 3;
+      if (nr > 1 || nc > 1) continue;
+      lists[2].off[n] = pw * (TROW + TSZ);
+      lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
+    }
+    lists[2].n = n;
+    // ---- ring fetch list, in consumption order: everything that is not in the two staged tiles
+    int nf = 0;
+    auto add = [&](const void* p, int bytes) {
+      fl[nf].src = reinterpret_cast<const char*>(p);
+      fl[nf].bytes = bytes;
+      nf++;
+    };
+    for (int seg = diag ? 1 : 0; seg < 2; seg++)
+      for (int i = 0; i < lists[seg].n; i++) add(in + (seg == 0 ? tJ : tI) + lists[seg].off[i], 9 * LC_ROWB);
+    for (int i = 0; i < lists[2].n; i++) add(in + tI + lists[2].off[i], 9 * LC_ROWB);
+    if (s.stage != 1) add(s.y + base + tI, 9 * LC_ROWB);  // stage 1: y is the stage input itself (tile B)
+    if (greal) add(a.Gre + tI, 9 * LC_TS * 8);
+    else add(a.G + tI, 9 * LC_ROWB);
+    if (s.stage == 4) {
+      add(s.y1 + base + tI, 9 * LC_ROWB);
+      add(s.y2 + base + tI, 9 * LC_ROWB);
+    }
+    *nfetch_p = nf;
+  }
+  {
+    const double2* src = a.ctab + ((long long)set * a.B + b) * a.NC;
+    for (int i = threadIdx.x; i < a.NC; i += 32 * LC_WARPS) ct[i] = __ldg(src + i);
+  }
+  __syncwarp();
+  const int nfetch = *nfetch_p;
+  auto issue = [&](int k) {  // fill ring slot k % LC_NBUF with fetch k (lane 0)
+    if (lane == 0) {
+      const LcFetch f = fl[k];
+      const int slot = k % LC_NBUF;
+      const unsigned mb = lc_smem_u32(mbars + slot);
+      lc_mbar_expect_tx(mb, (unsigned)f.bytes);
+      lc_bulk_g2s(lc_smem_u32(ring + (size_t)slot * LC_SLOTB), f.src, (unsigned)f.bytes, mb);
+    }
+  };
+  int kc = 0;  // next fetch to consume
+#pragma unroll 1
+  for (int k = 0; k < LC_NBUF && k < nfetch; k++) issue(k);
+  auto acquire = [&]() -> const double2* {
+    const int slot = kc % LC_NBUF;
+    lc_mbar_wait(lc_smem_u32(mbars + slot), (unsigned)((kc / LC_NBUF) & 1));
+    return reinterpret_cast<const double2*>(ring + (size_t)slot * LC_SLOTB) + cl;
+  };
+  auto release = [&]() {
+    __syncwarp();
+    if (kc + LC_NBUF < nfetch) issue(kc + LC_NBUF);
+    kc++;
+  };
+  __syncthreads();  // coefficient table and lists of every warp are in place
+  const double2* cJ12 = ct + 4 * NQ + (1 * 2 + 0) * 4;
+  double2 acc[9];
+#pragma unroll 1
+  for (int seg = diag ? 1 : 0; seg < 3; seg++) {
+    if (seg < 2) {
+      lc_mbar_wait(lc_smem_u32(tbar + seg), 0);
+      const double2* tp = (seg == 0 ? tileA : tileB) + 9 * g * LC_TS + cl;  // this warp's rows, this lane's column
+      lc_zero9(acc);
+      lc_s_in_group<NQ, XLOW>(acc, tp, ct);
+      // J_12 from the sibling groups of the same staged tile
+      if (g <= 1) lc_s_apply6<3>(acc, tp + 9 * LC_TS, cJ12[(0 * 2 + 0) * 2 + g], cJ12[(0 * 2 + 1) * 2 + g]);
+      if (g >= 1) lc_s_apply6<0>(acc, tp - 6 * LC_TS, cJ12[(1 * 2 + 0) * 2 + g - 1], cJ12[(1 * 2 + 1) * 2 + g - 1]);
+    } else {
+      // two-sided terms of the sites inside the tile, from the staged (I, J) tile: rho[r + 3^q, c + 3^q]
+      const double2 z = make_double2(0.0, 0.0);
+      for (int k = 0; k < a.n2; k++) {
+        const int q = a.two_q[k];
+        if (q > 2 || (q == 2 && g > 1)) continue;
+        const int wb = a.w_base + k * 4;
+        const int xl = q == 0 ? cl % 3 : (q == 1 ? (cl / 3) % 3 : cl / 9);
+        const bool ok = xl <= 1;
+        const int xx = ok ? xl : 0;
+        const int sh = q == 0 ? 1 : (q == 1 ? 3 : 9);
+        // lanes whose digit is 2 have no term: they read their own column (finite data) with a zero coefficient
+        const double2* wp = tileB + (9 * g + sh) * LC_TS + (ok ? cl + sh : cl);
+        if (q == 0) lc_s_apply_digit9<0>(acc, wp, ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 1) lc_s_apply_digit9<1>(acc, wp, ok ? ct[wb + xx] : z, ok ? ct[wb + 2 + xx] : z);
+        if (q == 2) lc_s_apply9(acc, wp, ok ? ct[wb + 2 * g + xx] : z);
+      }
+    }
+    {
+      const LcList* L = lists + seg;
+      const int n = L->n;
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        const double2* bp = acquire();
+        lc_s_apply9(acc, bp, ct[L->slot[i]]);
+        release();
+      }
+    }
+    if (seg == 0 || (seg == 1 && diag)) {
+      if (seg == 0) __syncthreads();  // every warp is done with tile A before M_JI overwrites it
+      if (active) {
+#pragma unroll
+        for (int t = 0; t < 9; t++) sT[(9 * g + t) * LC_T + lane] = acc[t];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- epilogue
+  {
+    double2 y0[9];
+    const double2* vp = tileB + 9 * g * LC_TS + cl;  // the stage input itself
+    if (s.stage != 1) {
+      const double2* bp = acquire();
+#pragma unroll
+      for (int t = 0; t < 9; t++) y0[t] = bp[t * LC_TS];
+      release();
+    } else {
+#pragma unroll
+      for (int t = 0; t < 9; t++) y0[t] = vp[t * LC_TS];
+    }
+    double2 k9[9];
+    {
+      const double2* bp = acquire();
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        double2 gg;
+        if (greal) gg = make_double2(reinterpret_cast<const double*>(bp - cl)[t * LC_TS + cl], 0.0);
+        else gg = bp[t * LC_TS];
+        const double2 m = sT[cl * LC_T + 9 * g + t];  // M_JI(J*27 + lane, I*27 + 9g + t)
+        double2 k = make_double2(acc[t].x + m.x, acc[t].y - m.y);
+        lc_cfma(k, gg, vp[t * LC_TS]);
+        k9[t] = k;
+      }
+      release();
+    }
+    const double h = s.stage == 3 ? s.h : 0.5 * s.h, t3 = 1.0 / 3.0, h6 = s.h * (1.0 / 6.0);
+    double2 res[9];
+    if (s.stage != 4) {
+#pragma unroll
+      for (int t = 0; t < 9; t++) res[t] = make_double2(fma(h, k9[t].x, y0[t].x), fma(h, k9[t].y, y0[t].y));
+    } else {
+      const double2* b1 = acquire();
+      double2 w[9];
+#pragma unroll
+      for (int t = 0; t < 9; t++) w[t] = b1[t * LC_TS];
+      release();
+      const double2* b2 = acquire();
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        const double2 v2 = b2[t * LC_TS], v3 = vp[t * LC_TS];
+        res[t] = make_double2(fma(h6, k9[t].x, t3 * (w[t].x + 2.0 * v2.x + v3.x - y0[t].x)),
+                              fma(h6, k9[t].y, t3 * (w[t].y + 2.0 * v2.y + v3.y - y0[t].y)));
+      }
+      release();
+    }
+    if (active) {
+      double2* outp = s.out + base + tI + lane;
+#pragma unroll
+      for (int t = 0; t < 9; t++) {
+        outp[t * RS] = res[t];
+        if (!diag) sT[lane * LC_T + 9 * g + t] = res[t];
+      }
+    }
+  }
+  if (diag) return;
+  __syncthreads();
+  if (active) {
+    const long long om = base + tJ + lane;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const double2 r = sT[(9 * g + t) * LC_T + lane];
+      s.out[om + t * RS] = make_double2(r.x, -r.y);
     }
   }
 }

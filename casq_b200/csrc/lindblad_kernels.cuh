@@ -135,9 +135,15 @@ struct LbStage {
 };
 
 // rho0 broadcast / copy into the (row-padded) working buffer
-// Column c of a density matrix sits at storage column lb_col(c): the generic path stores rows contiguously (tpad = 0), the
-// chain path pads every 27-column tile to 32 (tw = 27, tpad = 5) so that tile rows are 128 B aligned.
-__device__ __forceinline__ int lb_col(int c, int tw, int tpad) { return tpad ? c + (c / tw) * tpad : c; }
+// Element (r, c) of a density matrix sits at lb_idx(r, c) inside its [d * ld] buffer.  The generic path stores rows
+// contiguously (tpad = 0: r * ld + c); the chain path stores TILE-MAJOR (tw = 27, tpad = 5): 27 x 27 tiles, each padded to 27
+// rows of 32 elements and contiguous in memory (13.8 kB), tiles in row-major order -- a nine-row group of a tile is one
+// contiguous 4.6 kB piece, which one bulk asynchronous copy moves.
+__device__ __forceinline__ long long lb_idx(int r, int c, int ld, int tw, int tpad) {
+  if (!tpad) return (long long)r * ld + c;
+  const int ts = tw + tpad, nt = ld / ts;
+  return ((long long)(r / tw) * nt + c / tw) * (tw * ts) + (r % tw) * ts + c % tw;
+}
 
 __global__ void lindblad_init_kernel(int d, int ld, long long B, const double2* __restrict__ rho0, int batched,
                                      double2* __restrict__ y, int tw = 1, int tpad = 0) {
@@ -146,7 +152,7 @@ __global__ void lindblad_init_kernel(int d, int ld, long long B, const double2* 
   if (i >= n_per * B) return;
   const long long b = i / n_per, e = i - b * n_per;
   const int r = (int)(e / d), c = (int)(e - (long long)r * d);
-  y[(b * d + r) * ld + lb_col(c, tw, tpad)] = batched ? rho0[i] : rho0[e];
+  y[b * (long long)d * ld + lb_idx(r, c, ld, tw, tpad)] = batched ? rho0[i] : rho0[e];
 }
 
 // Observables at one output time: dressed-basis populations p_i = (V^+ rho_lab V)_ii with
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(256) lindblad_pops_kernel(int d, int ld, const
     for (int bc = 0; bc < d; bc++) {
       const double2 v = V[bc * d + i], p = ph[bc];
       const double2 w = make_double2(v.x * p.x + v.y * p.y, v.y * p.x - v.x * p.y);  // V[b,i] conj(ph_b)
-      const double2 x = R[(long long)arow * ld + lb_col(bc, tw, tpad)];
+      const double2 x = R[lb_idx(arow, bc, ld, tw, tpad)];
       sx += x.x * w.x - x.y * w.y;
       sy += x.x * w.y + x.y * w.x;
     }
@@ -188,5 +194,5 @@ __global__ void lindblad_copy_out_kernel(int d, int ld, long long B, const doubl
   if (i >= n_per * B) return;
   const long long b = i / n_per, e = i - b * n_per;
   const int r = (int)(e / d), c = (int)(e - (long long)r * d);
-  out[(b * T + t_slot) * n_per + e] = y[(b * d + r) * ld + lb_col(c, tw, tpad)];
+  out[(b * T + t_slot) * n_per + e] = y[b * (long long)d * ld + lb_idx(r, c, ld, tw, tpad)];
 }

@@ -229,3 +229,24 @@ def test_lindblad_d243_cfg4_operators_vs_oracle(scale, rho0_kind, monkeypatch):
         assert np.abs(got[:, -1] - np.conj(np.swapaxes(got[:, -1], -1, -2))).max() < 1e-13
         ref_pops = np.real(np.einsum("btii->bti", O.postprocess_density_matrices(om, np.array(span), want, normalize=False)))
         assert np.abs(pops.cpu().numpy() - ref_pops).max() < TOL_RHO
+
+
+@pytest.mark.parametrize("variant", ["CASQ_LB_NO_TMA", "CASQ_LB_GENERIC"])
+def test_lindblad_other_kernel_variants_keep_parity(variant, monkeypatch):
+    """The default chain kernel stages its operands with bulk asynchronous copies (TMA).  The same stage with plain loads
+    (CASQ_LB_NO_TMA) and the generic shift-class kernel (CASQ_LB_GENERIC: what a model that is not a chain of three-level
+    sites runs) must give the same answers: d = 81 against the dense oracle, and against the default path to rounding."""
+    rng = np.random.default_rng(811)
+    om, nm, ch = _chain_problem([0, 1, 2, 3], 1e3)
+    B, dur = 3, 8
+    p = dict(amp=rng.uniform(0.2, 0.9, B), angle=rng.uniform(-1, 1, B), sigma=3.0, beta=rng.uniform(-2, 2, B))
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [p])
+    rho0 = _random_density_matrices(rng, B, 81)
+    span = (0.0, 3 * DT)
+    want = np.concatenate([O.lindblad_rk4_solve(om, samples[b:b + 1], rho0[b], span, DT / 4)[1] for b in range(B)])
+    args = (nm, [("drag", ch.index("d0"), 0, dur)], engine.pack_params([p], device="cuda"), rho0, span, DT / 4)
+    default, _ = engine.solve_lindblad_rk4(*args)
+    monkeypatch.setenv(variant, "1")
+    other, _ = engine.solve_lindblad_rk4(*args)
+    assert np.abs(other.cpu().numpy() - want).max() < TOL_RHO
+    assert float((other - default).abs().max()) < 1e-13
