@@ -323,13 +323,20 @@ def run_configs(ctx) -> dict:
     pops = keep["r"][1][:, -1]
     bytes4 = 8.0 * 243 * 243 * 16 * 1028 * B4  # 4 stages x (read rho + write k) = 7.558 MB per step
     peak, src = _hbm_peak()
+    traffic4 = None
+    try:
+        traffic4 = json.load(open(os.path.join(ROOT, "profiles", "r02_lindblad_dram_bytes.json")))["dram_bytes_per_step"]
+    except Exception:
+        pass
     r4 = {"workload": "cfg4: full ibmq_manila d=243, T1=100us T2=80us per qubit, DRAG(256) on d0, RK4 max_dt=dt/4 (S=1028), "
                       "RWA 0.75 d0, 128 density matrices per GPU", "B_per_gpu": B4, "steps": 1028,
           "value": B4 * world / (ms * 1e-3), "unit": "trajectories/s", "ms": ms,
           "trace_defect": float((pops.sum(-1) - 1).abs().max()),
           "roofline": {"bound": "hbm", "achieved": bytes4 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                       "frac": bytes4 / (ms * 1e-3) / 1e9 / peak, "traffic": None, "bytes_per_step_model": 7.558e6,
-                       "peak_source": src, "kernel": "lindblad stage kernels (4 launches per RK4 step)"}}
+                       "frac": bytes4 / (ms * 1e-3) / 1e9 / peak, "traffic": traffic4,
+                       "traffic_unit": "DRAM bytes per RK4 step (4 stage launches) at B = 128, ncu; algorithmic: 7.558e6 x 128",
+                       "bytes_per_step_model": 7.558e6, "peak_source": src,
+                       "kernel": "lindblad_chain_tma_kernel<5,1> (4 launches per RK4 step) + lindblad_chain_coef_kernel"}}
     if ctx["cpu"]:
         n_s = 12
         sec, rho_o = cpu_cfg4(n_s)
@@ -549,7 +556,7 @@ def run_ours(args) -> None:
         flops = FLOP_PER_STEP * STEPS_PER_TRAJ * B
         achieved = flops / (ms_kernel * 1e-3) / 1e12
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_sv_rk4_small_dram_bytes.json")
+        prof = os.path.join(ROOT, "profiles", "r02_sv_rk4_small_dram_bytes.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch")
