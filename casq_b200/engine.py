@@ -84,24 +84,8 @@ def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_
     slots: [(kind, channel_index, start, duration)]; params: CUDA float64 [n_slots, 6, B];
     y0: [d] or [B, d] (numpy or torch, lab basis).
     """
-    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
-    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("solve_sv_rk4: params must be a CUDA float64 tensor [n_slots, 6, B]")
-    params = params.contiguous()
-    slots = list(slots)
-    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
-        raise CasqError(f"solve_sv_rk4: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
-    B = params.shape[2]
-    d = model.dim
-    y0_t = torch.as_tensor(np.asarray(y0) if not isinstance(y0, torch.Tensor) else y0).to(torch.complex128)
-    if y0_t.shape not in ((d,), (B, d)):
-        raise CasqError(f"solve_sv_rk4: y0 must be [{d}] or [{B},{d}], got {tuple(y0_t.shape)}")
-    y0_t = y0_t.to(dev).contiguous()
-    if t_eval is None:
-        T, te_ptr, te = 2, None, None
-    else:
-        te = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64))
-        T, te_ptr = len(te), te.ctypes.data
+    dev, params, slots, B, d, y0_t, T, te = _prep_solve(model, slots, params, y0, t_eval, "solve_sv_rk4")
+    te_ptr = None if te is None else te.ctypes.data
     if out is None:
         out = torch.empty((B, T, d), dtype=torch.complex128, device=dev)
     elif out.shape != (B, T, d) or out.dtype != torch.complex128 or not out.is_cuda or not out.is_contiguous():
@@ -117,7 +101,8 @@ def solve_sv_rk4(model: _native.NativeModel, slots, params: torch.Tensor, y0, t_
     return out
 
 
-def _prep_solve(model, slots, params, y0, t_eval, what):
+def _check_params(model, slots, params, what):
+    """Shared argument check of the batched solves -> (device, contiguous params [n_slots, 6, B], slot list, B)."""
     dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
     if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
         raise CasqError(f"{what}: params must be a CUDA float64 tensor [n_slots, 6, B]")
@@ -125,7 +110,12 @@ def _prep_solve(model, slots, params, y0, t_eval, what):
     slots = list(slots)
     if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
         raise CasqError(f"{what}: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
-    B, d = params.shape[2], model.dim
+    return dev, params, slots, params.shape[2]
+
+
+def _prep_solve(model, slots, params, y0, t_eval, what):
+    dev, params, slots, B = _check_params(model, slots, params, what)
+    d = model.dim
     y0_t = torch.as_tensor(np.asarray(y0) if not isinstance(y0, torch.Tensor) else y0).to(torch.complex128)
     if y0_t.shape not in ((d,), (B, d)):
         raise CasqError(f"{what}: y0 must be [{d}] or [{B},{d}], got {tuple(y0_t.shape)}")
@@ -164,14 +154,8 @@ def solve_sv_dopri5(model: _native.NativeModel, slots, params: torch.Tensor, y0,
 def propagators_expm(model: _native.NativeModel, slots, params: torch.Tensor, t_span, max_dt: float) -> torch.Tensor:
     """Exponential-midpoint propagators for a batch of pulse points: CUDA complex128 [B, d, d]
     (rotating frame, lab basis).  One expm (scaling-and-squaring Pade) per step of the fixed-step grid."""
-    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
-    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("propagators_expm: params must be a CUDA float64 tensor [n_slots, 6, B]")
-    params = params.contiguous()
-    slots = list(slots)
-    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
-        raise CasqError(f"propagators_expm: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
-    B, d = params.shape[2], model.dim
+    dev, params, slots, B = _check_params(model, slots, params, "propagators_expm")
+    d = model.dim
     out = torch.empty((B, d, d), dtype=torch.complex128, device=dev)
     with torch.cuda.device(dev):
         _native.check(
@@ -189,14 +173,8 @@ def solve_lindblad_rk4(model: _native.NativeModel, slots, params: torch.Tensor, 
 
     rho0: [d] state vector, [d,d] or [B,d,d] density matrix (lab frame).  Returns (rho [B,T,d,d] in the rotating
     frame or None, pops [B,T,d] dressed-basis populations after frame removal or None)."""
-    dev = _require_cuda(params.device if isinstance(params, torch.Tensor) and params.is_cuda else model.device)
-    if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64):
-        raise CasqError("solve_lindblad_rk4: params must be a CUDA float64 tensor [n_slots, 6, B]")
-    params = params.contiguous()
-    slots = list(slots)
-    if params.dim() != 3 or params.shape[1] != _native.NPARAM or params.shape[0] != max(1, len(slots)):
-        raise CasqError(f"solve_lindblad_rk4: params shape {tuple(params.shape)} does not match {len(slots)} slot(s)")
-    B, d = params.shape[2], model.dim
+    dev, params, slots, B = _check_params(model, slots, params, "solve_lindblad_rk4")
+    d = model.dim
     r0 = torch.as_tensor(np.asarray(rho0) if not isinstance(rho0, torch.Tensor) else rho0).to(torch.complex128)
     if r0.shape == (d,):
         r0 = torch.outer(r0, r0.conj())
