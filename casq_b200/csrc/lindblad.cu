@@ -268,7 +268,7 @@ static ChainPlan lc_analyze(const casq_model* m, Builder& bld, const std::vector
   for (int s = 0; s < NX + NJ; s++) put(reps[s]);
   for (const auto& r : ureps) put(r);
   // G[r,c] = A_rr + conj(A_cc) + sum over diagonal L_j of l_j(r) conj(l_j(c))
-  const int ld = (d / LC_T) * LC_TS;  // the chain path's padded-tile storage (lb_col)
+  const int ld = (d / LC_T) * LC_TS;  // the chain path's tile-major storage (lb_idx)
   P.G.assign((size_t)d * ld, cplx(0.0));
   for (int r = 0; r < d; r++)
     for (int c = 0; c < d; c++) {
@@ -286,7 +286,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
                               int n_total, int64_t B, const double* params_dev, const double* rho0_dev, int rho0_batched,
                               double t0, double t1, double max_dt, int T, const double* t_eval, double* out_rho_dev,
                               double* out_pops_dev, cudaStream_t st) {
-  const int d = m->d, ld = (d / LC_T) * LC_TS;  // tile-major storage, 27-column tiles padded to 32 (lb_idx): d * ld elements per matrix
+  const int d = m->d, ld = (d / LC_T) * LC_TS;  // tile-major storage (lb_idx): d * ld elements per matrix
   const int tw = LC_T, tpad = LC_TS - LC_T;
   int rc;
   TimeGrid g;
@@ -321,7 +321,8 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   const size_t o_G = off; off = align16(off + (size_t)d * ld * 16);
   bool g_real = true;
   for (const cplx& gv : cp.G) g_real = g_real && gv.imag() == 0.0;
-  const size_t o_Gre = off; off = align16(off + (g_real ? (size_t)d * ld * 8 : 16));
+  const size_t n_gre = (size_t)(d / LC_T) * (d / LC_T) * LC_T * LC_GS;  // real table: tile-major with row stride LC_GS
+  const size_t o_Gre = off; off = align16(off + (g_real ? n_gre * 8 : 16));
   const size_t o_pij = off; off = align16(off + pair_ij.size() * sizeof(int));
   const size_t o_ss = off; off = align16(off + cp.slot_start.size() * sizeof(int));
   const size_t o_av = off; off = align16(off + std::max<size_t>(cp.atom_val.size(), 1) * 16);
@@ -344,7 +345,12 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   memcpy(&blob[o_G], cp.G.data(), (size_t)d * ld * 16);
   if (g_real) {
     double* gr = reinterpret_cast<double*>(&blob[o_Gre]);
-    for (size_t i = 0; i < (size_t)d * ld; i++) gr[i] = cp.G[i].real();
+    const int nt = d / LC_T;
+    for (int r = 0; r < d; r++)
+      for (int c2 = 0; c2 < d; c2++) {
+        const size_t tile = (size_t)(r / LC_T) * nt + c2 / LC_T;
+        gr[tile * (LC_T * LC_GS) + (r % LC_T) * LC_GS + c2 % LC_T] = cp.G[tile * (LC_T * LC_TS) + (r % LC_T) * LC_TS + c2 % LC_T].real();
+      }
   }
   memcpy(&blob[o_pij], pair_ij.data(), pair_ij.size() * sizeof(int));
   memcpy(&blob[o_ss], cp.slot_start.data(), cp.slot_start.size() * sizeof(int));

@@ -23,7 +23,10 @@
 #include "lindblad_stage.cuh"
 
 #define LC_T 27          // tile edge = 3 sites
-#define LC_TS 32         // storage stride of a tile's columns: 27 used + 5 padding, so that every tile row starts on a 128 B line
+#ifndef LC_TS
+#define LC_TS 27         // storage stride of a tile row.  27 = no padding: bulk copies need 16 B alignment only, and padding to 32
+#endif                   // (128 B aligned rows, a gain for neither kernel) costs 18 % more HBM / L2 / shared-memory bytes
+#define LC_GS ((LC_TS + 1) & ~1)  // row stride of the REAL diagonal-coefficient table (doubles): keeps every nine-row group 16 B aligned
 #define LC_WARPS 3       // warps per block = per tile pair: warp g owns the rows with x_2 = g
 #define LC_MAXQ 6        // sites
 #ifndef LC_MINBLOCKS
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
     double2* outp = s.out + ob;
     const bool greal = a.Gre != nullptr;
     const double2* gp = a.G + o0;
-    const double* grp = greal ? a.Gre + o0 : nullptr;
+    const double* grp = greal ? a.Gre + ((long long)I * NT + J) * (LC_T * LC_GS) + 9 * g * LC_GS + cl : nullptr;
     const double h = s.stage == 3 ? s.h : 0.5 * s.h, t3 = 1.0 / 3.0, h6 = s.h * (1.0 / 6.0);
 #pragma unroll
     for (int t0 = 0; t0 < 9; t0 += 3) {  // three rows at a time: nine or more independent loads in flight
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
       for (int u = 0; u < 3; u++) {
         y0[u] = yp[(t0 + u) * RS];
         v[u] = __ldg(p + (t0 + u) * RS);
-        gg[u] = greal ? make_double2(__ldg(grp + (t0 + u) * RS), 0.0) : __ldg(gp + (t0 + u) * RS);
+        gg[u] = greal ? make_double2(__ldg(grp + (t0 + u) * LC_GS), 0.0) : __ldg(gp + (t0 + u) * RS);
       }
 #pragma unroll
       for (int u = 0; u < 3; u++) {
@@ -358,12 +361,12 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_MINBLOCKS) lindblad_chain_st
 //     samples on the load scoreboard at every occupancy from 12 to 21 warps per SM).
 // The fetch list of a warp is built in consumption order by its lane 0; lanes 0..8 issue one row copy each.
 #ifndef LC_NBUF
-#define LC_NBUF 3
+#define LC_NBUF 2
 #endif
 #ifndef LC_TMA_MINBLOCKS
-#define LC_TMA_MINBLOCKS 3  // shared memory (74 kB per block) allows three blocks per SM
+#define LC_TMA_MINBLOCKS 4  // shared memory (50 kB per block with two ring slots per warp) allows four blocks = 12 warps per SM
 #endif
-#define LC_ROWB (LC_TS * 16)       // bytes of one staged row (a tile row: 27 complex + 5 padding)
+#define LC_ROWB (LC_TS * 16)       // bytes of one staged row (a tile row)
 #define LC_SLOTB (9 * LC_ROWB)     // one ring slot: nine rows = one contiguous piece of the tile-major storage
 #define LC_MAXFETCH 48
 
@@ -401,7 +404,7 @@ __device__ __forceinline__ void lc_bulk_g2s(unsigned dst, const void* src, unsig
 
 // shared memory of a block: [tile A: (J, I) tile of the stage input, later M_JI^T / the result tile][tile B: (I, J) tile]
 // [coefficient table][gather lists][per warp: ring of LC_NBUF slots, fetch list, mbarriers]
-#define LC_TILEB (LC_T * LC_ROWB)  // one staged tile: 27 rows of 32 elements
+#define LC_TILEB (LC_T * LC_ROWB)  // one staged tile
 static inline size_t lindblad_chain_tma_smem(int NC) {
   return 2 * (size_t)LC_TILEB + (size_t)((NC + 1) & ~1) * 16 + 3 * LC_WARPS * sizeof(LcList) + 64 +
          LC_WARPS * ((size_t)LC_NBUF * LC_SLOTB + LC_MAXFETCH * sizeof(LcFetch) + 64);
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_TMA_MINBLOCKS) lindblad_chai
       for (int i = 0; i < lists[seg].n; i++) add(in + (seg == 0 ? tJ : tI) + lists[seg].off[i], 9 * LC_ROWB);
     for (int i = 0; i < lists[2].n; i++) add(in + tI + lists[2].off[i], 9 * LC_ROWB);
     if (s.stage != 1) add(s.y + base + tI, 9 * LC_ROWB);  // stage 1: y is the stage input itself (tile B)
-    if (greal) add(a.Gre + tI, 9 * LC_TS * 8);
+    if (greal) add(a.Gre + ((long long)I * NT + J) * (LC_T * LC_GS) + 9 * g * LC_GS, 9 * LC_GS * 8);
     else add(a.G + tI, 9 * LC_ROWB);
     if (s.stage == 4) {
       add(s.y1 + base + tI, 9 * LC_ROWB);
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_TMA_MINBLOCKS) lindblad_chai
 #pragma unroll
       for (int t = 0; t < 9; t++) {
         double2 gg;
-        if (greal) gg = make_double2(reinterpret_cast<const double*>(bp - cl)[t * LC_TS + cl], 0.0);
+        if (greal) gg = make_double2(reinterpret_cast<const double*>(bp - cl)[t * LC_GS + cl], 0.0);
         else gg = bp[t * LC_TS];
         const double2 m = sT[cl * LC_T + 9 * g + t];  // M_JI(J*27 + lane, I*27 + 9g + t)
         double2 k = make_double2(acc[t].x + m.x, acc[t].y - m.y);

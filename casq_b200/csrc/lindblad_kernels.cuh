@@ -136,11 +136,11 @@ struct LbStage {
 
 // rho0 broadcast / copy into the (row-padded) working buffer
 // Element (r, c) of a density matrix sits at lb_idx(r, c) inside its [d * ld] buffer.  The generic path stores rows
-// contiguously (tpad = 0: r * ld + c); the chain path stores TILE-MAJOR (tw = 27, tpad = 5): 27 x 27 tiles, each padded to 27
-// rows of 32 elements and contiguous in memory (13.8 kB), tiles in row-major order -- a nine-row group of a tile is one
-// contiguous 4.6 kB piece, which one bulk asynchronous copy moves.
+// contiguously (tw = 1: r * ld + c); the chain path stores TILE-MAJOR (tw = 27, tpad = LC_TS - 27): 27 x 27 tiles, each
+// stored as 27 rows of tw + tpad elements and contiguous in memory, tiles in row-major order -- a nine-row group of a tile
+// is one contiguous piece (3.9 kB), which one bulk asynchronous copy moves.
 __device__ __forceinline__ long long lb_idx(int r, int c, int ld, int tw, int tpad) {
-  if (!tpad) return (long long)r * ld + c;
+  if (tw <= 1) return (long long)r * ld + c;
   const int ts = tw + tpad, nt = ld / ts;
   return ((long long)(r / tw) * nt + c / tw) * (tw * ts) + (r % tw) * ts + c % tw;
 }
