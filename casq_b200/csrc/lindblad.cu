@@ -327,6 +327,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   const size_t o_ss = off; off = align16(off + cp.slot_start.size() * sizeof(int));
   const size_t o_av = off; off = align16(off + std::max<size_t>(cp.atom_val.size(), 1) * 16);
   const size_t o_ac = off; off = align16(off + std::max<size_t>(cp.atom_code.size(), 1) * sizeof(int));
+  const size_t o_plan = off; off = align16(off + (size_t)npairs * LC_WARPS * 3 * sizeof(LcList));  // written by the plan kernel
   std::vector<unsigned char> blob(off, 0);
   if (NTF) {
     memcpy(&blob[o_tfsig], tf_sig.data(), NTF * sizeof(int));
@@ -408,6 +409,7 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   c.slot_start = (const int*)(dev + o_ss);
   c.atom_val = (const double2*)(dev + o_av);
   c.atom_code = (const int*)(dev + o_ac);
+  c.plan = dev + o_plan;
   const size_t smem_coef = (size_t)std::max(NTF, 1) * 16;
   const bool low_only = (cp.drv_mask & 6u) == 0;  // only site 0 of the low three is driven (cfg 4): leaner in-tile code
   CASQ_CUDA(cudaFuncSetAttribute(lindblad_chain_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_coef));
@@ -426,6 +428,16 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
   const size_t smem_tma = lindblad_chain_tma_smem(cp.NC), smem_ldg = lindblad_chain_smem(cp.NC);
   CASQ_CUDA(cudaFuncSetAttribute(fn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
   CASQ_CUDA(cudaFuncSetAttribute(fn_ldg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ldg));
+  {
+    const dim3 pg((unsigned)npairs), pb(32);
+    switch (cp.nq) {
+      case 3: lindblad_chain_plan_kernel<3><<<pg, pb, 0, st>>>(c, (LcList*)(dev + o_plan)); break;
+      case 4: lindblad_chain_plan_kernel<4><<<pg, pb, 0, st>>>(c, (LcList*)(dev + o_plan)); break;
+      case 5: lindblad_chain_plan_kernel<5><<<pg, pb, 0, st>>>(c, (LcList*)(dev + o_plan)); break;
+      default: lindblad_chain_plan_kernel<6><<<pg, pb, 0, st>>>(c, (LcList*)(dev + o_plan)); break;
+    }
+    CASQ_CUDA(cudaGetLastError());
+  }
   int tma_stages = LC_DEFAULT_TMA_STAGES;
   if (const char* e = getenv("CASQ_LB_TMA_STAGES")) tma_stages = atoi(e) & 15;
   if (getenv("CASQ_LB_NO_TMA")) tma_stages = 0;

@@ -56,6 +56,7 @@ struct LcArgs {
   const int* slot_start;
   const double2* atom_val;
   const int* atom_code;
+  const void* plan;           // [npairs][3 warps][3 segments] LcList: the gather lists of every task, built once per solve
 };
 
 __device__ __forceinline__ void lc_cfma(double2& acc, const double2 c, const double2 v) {
@@ -453,6 +454,35 @@ __device__ __forceinline__ void lc_s_apply_digit9(double2 (&acc)[9], const doubl
   }
 }
 
+// The gather lists depend on the tile pair and the row group only: one launch per solve writes them for every task shape.
+template <int NQ>
+__global__ void lindblad_chain_plan_kernel(const LcArgs a, LcList* plan) {
+  constexpr int D = lc_pow3(NQ), NT = D / LC_T, RS = LC_TS, TSZ = LC_T * LC_TS, TROW = NT * TSZ;
+  const int pr = blockIdx.x, g = threadIdx.x;
+  if (pr >= a.npairs || g >= LC_WARPS) return;
+  const int I = a.pair_ij[2 * pr], J = a.pair_ij[2 * pr + 1];
+  LcList* lists = plan + ((size_t)pr * LC_WARPS + g) * 3;
+  if (I != J) lc_build_one_sided<NQ, RS, TROW>(lists + 0, J, g, a.drv_mask);
+  else lists[0].n = 0;
+  lc_build_one_sided<NQ, RS, TROW>(lists + 1, I, g, a.drv_mask);
+  int n = 0;
+  for (int k = 0; k < a.n2; k++) {  // two-sided terms of the sites in the tile INDEX: warp-uniform coefficient W(k, nr, nc)
+    const int q = a.two_q[k];
+    if (q <= 2) continue;
+    int pw = 1, ti = I, tj = J;
+    for (int sq = 3; sq < q; sq++) {
+      pw *= 3;
+      ti /= 3;
+      tj /= 3;
+    }
+    const int nr = ti % 3, nc = tj % 3;
+    if (nr > 1 || nc > 1) continue;
+    lists[2].off[n] = pw * (TROW + TSZ);
+    lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
+  }
+  lists[2].n = n;
+}
+
 template <int NQ, int XLOW>
 __global__ void __launch_bounds__(32 * LC_WARPS, LC_TMA_MINBLOCKS) lindblad_chain_tma_kernel(const LcArgs a, int set, const LbStage s) {
   constexpr int D = lc_pow3(NQ), NT = D / LC_T, LD = NT * LC_TS, RS = LC_TS, TSZ = LC_T * LC_TS, TROW = NT * TSZ;  // tile-major (lb_idx)
@@ -491,33 +521,19 @@ __global__ void __launch_bounds__(32 * LC_WARPS, LC_TMA_MINBLOCKS) lindblad_chai
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  {  // this warp's three gather lists (3 x 128 B) from the per-solve plan
+    const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const LcList*>(a.plan) + ((size_t)pr * LC_WARPS + g) * 3);
+    if (lane < (int)(3 * sizeof(LcList) / 16)) reinterpret_cast<int4*>(lists)[lane] = __ldg(src + lane);
+  }
+  __syncwarp();
   if (lane == 0) {
-    // the two tiles of the stage input: every warp brings its own nine rows (one contiguous 4.6 kB piece each)
+    // the two tiles of the stage input: every warp brings its own nine rows (one contiguous piece each)
     if (!diag) {
       lc_mbar_expect_tx(lc_smem_u32(tbar + 0), 9 * LC_ROWB);
       lc_bulk_g2s(lc_smem_u32(tileA + 9 * g * LC_TS), in + tJ, 9 * LC_ROWB, lc_smem_u32(tbar + 0));
     }
     lc_mbar_expect_tx(lc_smem_u32(tbar + 1), 9 * LC_ROWB);
     lc_bulk_g2s(lc_smem_u32(tileB + 9 * g * LC_TS), in + tI, 9 * LC_ROWB, lc_smem_u32(tbar + 1));
-    if (!diag) lc_build_one_sided<NQ, RS, TROW>(lists + 0, J, g, a.drv_mask);
-    else lists[0].n = 0;
-    lc_build_one_sided<NQ, RS, TROW>(lists + 1, I, g, a.drv_mask);
-    int n = 0;
-    for (int k = 0; k < a.n2; k++) {
-      const int q = a.two_q[k];
-      if (q <= 2) continue;
-      int pw = 1, ti = I, tj = J;
-      for (int sq = 3; sq < q; sq++) {
-        pw *= 3;
-        ti /= 3;
-        tj /= 3;
-      }
-      const int nr = ti % 3, nc = tj % 3;
-      if (nr > 1 || nc > 1) continue;
-      lists[2].off[n] = pw * (TROW + TSZ);
-      lists[2].slot[n++] = a.w_base + k * 4 + nr * 2 + nc;
-    }
-    lists[2].n = n;
     // ---- ring fetch list, in consumption order: everything that is not in the two staged tiles
     int nf = 0;
     auto add = [&](const void* p, int bytes) {
