@@ -222,3 +222,124 @@ def test_gate_fidelity_definitions():
     assert float(fa9[0]) == pytest.approx(1.0) and float(l9[0]) == pytest.approx(0.0)
     with pytest.raises(CasqError):
         gate_fidelities(torch.as_tensor(U9[None]), X, [3, 3])
+
+
+def _cpu_backend(qubits=(0,), **kw):
+    from casq_b200.backends import BackendLibrary, build
+    from casq_b200.models import ControlModel, TransmonModel
+
+    h = TransmonModel.manila(extracted_qubits=list(qubits))
+    c = ControlModel(dt=O.MANILA_DT, channel_carrier_freqs=O.MANILA_CARRIERS)
+    b = build(BackendLibrary.B200, h, c, seed=3)  # model construction is host-only work: no GPU needed
+    return type(b)(h, c, seed=3, **kw) if kw else b
+
+
+def test_schedule_phase_and_frequency_instructions_become_slot_parameters():
+    """ShiftPhase / SetPhase / ShiftFrequency / SetFrequency act on the LATER plays of their channel (qiskit-dynamics
+    InstructionToSignals): phases join the pulse angle, frequency shifts become the freq_shift row."""
+    from casq_b200.pulse import (ControlChannel, Drag, DriveChannel, Gaussian, Play, Schedule, SetFrequency, SetPhase,
+                                 ShiftFrequency, ShiftPhase)
+
+    backend = _cpu_backend()
+    s = Schedule()
+    s.insert(0, Play(Gaussian(duration=8, amp=0.2, sigma=2.0), DriveChannel(0)))       # before any shift: untouched
+    s.insert(8, ShiftPhase(0.25, DriveChannel(0)))
+    s.insert(8, ShiftFrequency(3e6, DriveChannel(0)))
+    s.insert(8, ShiftFrequency(1e6, ControlChannel(0)))                                 # other channel: no effect on d0
+    s.insert(8, Play(Drag(duration=8, amp=0.3, angle=0.5, sigma=2.0, beta=1.0), DriveChannel(0)))
+    s.insert(16, ShiftPhase(0.25, DriveChannel(0)))
+    s.insert(16, SetFrequency(O.MANILA_CARRIERS["d0"] - 2e6, DriveChannel(0)))
+    s.insert(16, Play(Gaussian(duration=8, amp=0.1, sigma=2.0), DriveChannel(0)))
+    s.insert(24, SetPhase(-1.0, DriveChannel(0)))
+    s.insert(24, Play(Gaussian(duration=8, amp=0.1, sigma=2.0), DriveChannel(0)))
+    slots, params = backend._slots_from_schedule(s)
+    assert [(k, st, d) for k, _, st, d in slots] == [("gaussian", 0, 8), ("drag", 8, 8), ("gaussian", 16, 8), ("gaussian", 24, 8)]
+    assert "freq_shift" not in params[0] and params[0]["angle"] == 0.0
+    assert float(params[1]["angle"]) == pytest.approx(0.75) and params[1]["freq_shift"] == pytest.approx(3e6)
+    assert float(params[2]["angle"]) == pytest.approx(0.5) and params[2]["freq_shift"] == pytest.approx(-2e6)
+    assert float(params[3]["angle"]) == pytest.approx(-1.0) and params[3]["freq_shift"] == pytest.approx(-2e6)
+    packed = engine_pack(params)
+    assert packed.shape == (4, 6, 1) and packed[1, 5, 0] == 3e6 and packed[0, 5, 0] == 0.0
+    with pytest.raises(CasqError, match="not in the Hamiltonian"):
+        bad = Schedule()
+        bad.insert(0, Play(Gaussian(duration=8, amp=0.2, sigma=2.0), DriveChannel(3)))
+        backend._slots_from_schedule(bad)
+
+
+def engine_pack(params):
+    from casq_b200 import engine
+
+    return engine.pack_params(params).numpy()
+
+
+def test_cross_resonance_gate_and_multi_qubit_circuit_host_logic():
+    from casq_b200.gates import CrossResonancePulseGate, DragPulseGate, PulseCircuit
+    from casq_b200.pulse import ControlChannel, GaussianSquare
+
+    gate = CrossResonancePulseGate(control_channel=1, duration=64, amplitude=0.4, angle=0.1, name="cr")
+    assert gate.num_qubits == 2 and gate.channel_name(0) == "u1" and gate.channel(5) == ControlChannel(1)
+    assert gate.to_parameters_dict(np.array([8.0, 20.0])) == {"sigma": 8.0, "width": 20.0}
+    pulse = gate.pulse({"sigma": 8.0, "width": 20.0})
+    assert isinstance(pulse, GaussianSquare) and pulse.duration == 64 and pulse.amp == 0.4 and pulse.angle == 0.1
+    sched = gate.schedule({"sigma": 8.0, "width": 20.0}, 0)
+    assert sched.channels == ["u1"] and sched.duration == 64
+    circuit = PulseCircuit(2, 2)
+    circuit.pulse_gate(gate, {"sigma": 8.0, "width": 20.0}, (0, 1))
+    circuit.pulse_gate(DragPulseGate(duration=16, amplitude=0.2, name="x"), {"sigma": 4.0, "beta": 0.0}, 1)
+    circuit.measure(0, 0)
+    circuit.measure(1, 1)
+    assert [i.qubits for i in circuit.data] == [(0, 1), (1,), (0,), (1,)]
+    with pytest.raises(CasqError, match="acts on 2"):
+        circuit.pulse_gate(gate, {"sigma": 8.0, "width": 20.0}, 0)
+    with pytest.raises(CasqError, match="width"):
+        gate.pulse({"sigma": 8.0, "width": 65.0})
+    # ASAP scheduling through the backend: the DRAG on qubit 1 starts when the CR gate (qubits 0 and 1) ends
+    backend = _cpu_backend((0, 1))
+    sched, t_acq, measured = backend._circuit_to_schedule(circuit)
+    assert t_acq == 80 and measured == [0, 1]
+    slots, params = backend._slots_from_schedule(sched)
+    ch = backend.hamiltonian.channels
+    assert slots == [("gaussian_square", ch.index("u1"), 0, 64), ("drag", ch.index("d1"), 64, 16)]
+
+
+def test_to_solution_forwarded_dims_density_matrix_and_iq_layout():
+    """_to_solution is host-only: populations / counts / IQ for one and two measured qubits, Statevector and DensityMatrix."""
+    from casq_b200.quantum_info import DensityMatrix, Statevector
+
+    rng = np.random.default_rng(0)
+    psi = rng.normal(size=9) + 1j * rng.normal(size=9)
+    psi /= np.linalg.norm(psi)
+    probs = np.abs(psi) ** 2
+    plain = _cpu_backend((0, 1))
+    fwd = _cpu_backend((0, 1), forward_subsystem_dims=True)
+    a = plain._to_solution("c", np.array([0.0, 1e-9]), np.array([psi, psi]), np.array([probs, probs]), 512, [0, 1])
+    assert a.qubits == [0] and a.populations[0] == pytest.approx({"0": probs[0], "1": probs[1:].sum()})
+    assert isinstance(a.states[0], Statevector) and a.states[0].dims() == (9,)
+    assert sum(a.counts[1].values()) == 512 and len(a.iq_data[0]) == 512 and len(a.avg_iq_data[0]) == 2
+    assert a.samples[0] == a.samples[1]  # same experiment seed at every time point (helpers.py:137-141)
+    b = fwd._to_solution("c", np.array([0.0]), np.array([psi]), np.array([probs]), 512, [0, 1])
+    assert b.qubits == [0, 1] and b.states[0].dims() == (3, 3)
+    assert b.populations[0] == pytest.approx(O.populations_dict(probs, subsystem_dims=[3, 3], measured=(0, 1)))
+    assert np.array(b.iq_data[0]).shape == (512, 2, 2) and np.array(b.avg_iq_data[0]).shape == (2, 2)
+    one = fwd._to_solution("c", np.array([0.0]), np.array([psi]), np.array([probs]), 256, [1])
+    assert one.qubits == [1] and one.populations[0] == pytest.approx(O.populations_dict(probs, subsystem_dims=[3, 3], measured=(1,)))
+    rho = np.outer(psi, psi.conj())
+    d = fwd._to_solution("c", np.array([0.0]), np.array([rho]), np.array([probs]), 128, [0], density=True)
+    assert isinstance(d.states[0], DensityMatrix) and d.states[0].dims() == (3, 3) and sum(d.counts[0].values()) == 128
+    with pytest.raises(CasqError, match="not in the Hamiltonian"):
+        fwd._to_solution("c", np.array([0.0]), np.array([psi]), np.array([probs]), 16, [4])
+
+
+def test_duration_sweep_assembly_on_cpu_tensors():
+    import torch
+    from casq_b200.backends.b200.b200_pulse_backend import BatchSolution, DurationSweepSolution
+
+    def part(n, dur):
+        return BatchSolution(times=np.array([0.0, dur * 1.0]), states=torch.full((n, 2, 3), float(dur), dtype=torch.complex128),
+                             probabilities=torch.full((n, 2, 3), float(dur), dtype=torch.float64),
+                             populations=torch.full((n, 2, 2), float(dur), dtype=torch.float64))
+
+    sol = DurationSweepSolution.assemble(5, {16: (np.array([0, 3]), part(2, 16)), 32: (np.array([1, 2, 4]), part(3, 32))})
+    assert sol.batch_size == 5 and sol.durations.tolist() == [16, 32, 32, 16, 32]
+    assert sol.times[:, 1].tolist() == [16.0, 32.0, 32.0, 16.0, 32.0]
+    assert sol.states[:, 0, 0].real.tolist() == [16.0, 32.0, 32.0, 16.0, 32.0] and sol.populations[3, 1, 1] == 16.0
