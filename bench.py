@@ -569,10 +569,10 @@ def run_ours(args) -> None:
             "config": workload_config(world),
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "trajectories/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 3 * args.steps,  # per step: stage-table kernel, slice-queue init kernel, RK4 kernel
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
-                         "kernel": "sv_rk4_small2_kernel<3,TRI> (2 trajectories per thread)", "kernel_ms": ms_kernel,
+                         "kernel": "sv_rk4_small2_kernel<3,TRI,SLICED> (2 trajectories per thread, time-sliced persistent grid)", "kernel_ms": ms_kernel,
                          "flop_per_step": FLOP_PER_STEP, "dense_model_flop_per_step": FLOP_PER_STEP_DENSE_MODEL,
                          "peak_source": "measured live: casq_fp64_fma_probe (MEASURED_PEAKS.json has no fp64 entry)"},
             "cpu_baseline": cpu,

@@ -75,7 +75,8 @@ struct casq_model {
   // cache key of the table currently resident in `tab`
   std::string tab_key;
   long long tab_NT = 0;   // shape of the cached fixed-step grid (small RK4 path)
-  int tab_n_pieces = 0;
+  int tab_n_pieces = 0, tab_piece0_steps = 0;
+  DeviceBuf slice_buf;    // ticket queue and hand-over state of the time-sliced headline kernel
   // second stream + fork/join events of the Lindblad path (several parts of the batch in flight fill each other's grid tails)
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};

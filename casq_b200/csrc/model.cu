@@ -265,7 +265,7 @@ extern "C" int casq_model_create(casq_model** out, int dim, int n_channels, cons
 extern "C" void casq_model_destroy(casq_model* m) {
   if (!m) return;
   DeviceBuf* bufs[] = {&m->tab, &m->tab_idx, &m->tab_times, &m->pieces_n, &m->pieces_h, &m->consts,
-                       &m->work0, &m->work1, &m->work2, &m->work3};
+                       &m->work0, &m->work1, &m->work2, &m->work3, &m->slice_buf};
   for (DeviceBuf* b : bufs) b->release();
   for (int i = 0; i < 3; i++) {
     if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);

@@ -16,6 +16,8 @@
 //    changes -- once per ~40 steps -- from the per-point parameters (amp, angle, sigma, width, beta).
 //  * operator sparsity is a compile-time property of the instantiation (TRI = tridiagonal ladder coupling,
 //    HAS_S = static/diagonal terms survive in the frame), so absent elements cost neither registers nor flops.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -27,6 +29,9 @@
 #define SMALL_MAXK 2
 #define SMALL_MAXE 6
 #define SMALL_CHUNK_STEPS 32
+#ifndef SMALL_SLICE_SLEEP_NS
+#define SMALL_SLICE_SLEEP_NS 50
+#endif
 
 struct SmallArgs {
   const double* table;  // [NT][W]
@@ -447,11 +452,52 @@ __device__ __noinline__ void small_env_refresh2(const SmallArgs* __restrict__ ap
 // RK4 chains are independent, so every stage offers twice the instruction-level parallelism to the fp64 pipe
 // while the table entry (shared by the whole batch) is loaded once for both.  Same arithmetic, same order per
 // trajectory as sv_rk4_small_kernel.
-template <int D, bool TRI>
-__global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
+//
+// SLICED (time slicing, B >= 16384 and one piece): the batch is 5.28 warp-units per scheduler on a B200 (1e5 points: 782
+// blocks for 888 resident block slots), so with one block per 128 trajectories for the whole time span some SMs carry six
+// blocks and some five, and the kernel takes the time of six (measured: 7.10 / 10.27 ms at exactly 2 / 3 warps per scheduler,
+// 10.29 ms at 2.64: the kernel is throughput bound and the busiest scheduler sets the time).  Here a PERSISTENT grid fills
+// every block slot and pulls (block of trajectories, segment of chunks) tasks from a ticket queue in global memory; the
+// state (17 doubles per thread) is handed over through global memory at segment boundaries and the task of the next
+// segment goes to the worker that has waited longest, so the idle slots rotate over the SMs and every scheduler carries
+// the same average load.  Same arithmetic in the same order: results are bit-identical to the unsliced kernel.
+struct SliceCtl {
+  unsigned* head;      // next ticket to hand out
+  unsigned* tail;      // next queue slot to fill
+  int* slot;           // [total] task = job * nseg + seg, by ticket
+  unsigned* flag;      // [total] 1 once slot[] is valid
+  double* state;       // [n_jobs * 64][17] y0r,y0i,y1r,y1i (4 D), env0, env1 (4), cur_idx
+  unsigned total;      // n_jobs * nseg
+  int n_jobs, nseg, chunks_per_seg;
+};
+
+template <int D, bool TRI, bool SLICED>
+__global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, const SliceCtl ctl) {
   typedef Entry<D, 1, false, false, TRI> Ent;
   const long long half = (a.B + 1) / 2;
-  const long long t_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_task;
+ for (;;) {  // SLICED: one iteration per task
+  int job = blockIdx.x, seg = 0;
+  if (SLICED) {
+    if (threadIdx.x == 0) {
+      const unsigned ticket = atomicAdd(ctl.head, 1u);
+      int task = -1;
+      if (ticket < ctl.total) {
+        volatile unsigned* f = ctl.flag + ticket;
+        while (*f == 0u) __nanosleep(SMALL_SLICE_SLEEP_NS);
+        __threadfence();
+        task = ((volatile int*)ctl.slot)[ticket];
+      }
+      s_task = task;
+    }
+    __syncthreads();
+    const int task = s_task;
+    __syncthreads();
+    if (task < 0) return;
+    job = task / ctl.nseg;
+    seg = task - job * ctl.nseg;
+  }
+  const long long t_raw = (long long)job * blockDim.x + threadIdx.x;
   const bool live0 = t_raw < half;
   const long long b0 = live0 ? t_raw : half - 1;
   const bool live1 = live0 && (b0 + half) < a.B;
@@ -474,8 +520,6 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
       yi[i] = si;
     }
   };
-  init(b0, y0r, y0i);
-  init(b1, y1r, y1i);
   int out_slot = 0;
   auto emit_one = [&](long long b, const double* yr, const double* yi) {
     double* o = a.out + (b * (long long)a.T + out_slot) * 2 * D;
@@ -498,11 +542,29 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
     if (live1) emit_one(b1, y1r, y1i);
     out_slot++;
   };
-  if (a.keep[0]) emit();
-
   int cur_idx = -2;
   dcplx env0, env1;
   env0.re = env0.im = env1.re = env1.im = 0.0;
+  double* const st_ptr = SLICED ? ctl.state + ((long long)job * 64 + threadIdx.x) * (4 * D + 5) : nullptr;
+  if (!SLICED || seg == 0) {
+    init(b0, y0r, y0i);
+    init(b1, y1r, y1i);
+    if (a.keep[0]) emit();
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      y0r[i] = __ldcg(st_ptr + i);
+      y0i[i] = __ldcg(st_ptr + D + i);
+      y1r[i] = __ldcg(st_ptr + 2 * D + i);
+      y1i[i] = __ldcg(st_ptr + 3 * D + i);
+    }
+    env0.re = __ldcg(st_ptr + 4 * D);
+    env0.im = __ldcg(st_ptr + 4 * D + 1);
+    env1.re = __ldcg(st_ptr + 4 * D + 2);
+    env1.im = __ldcg(st_ptr + 4 * D + 3);
+    cur_idx = (int)__ldcg(st_ptr + 4 * D + 4);
+    out_slot = a.keep[0] ? 1 : 0;
+  }
 
   constexpr int kChunk = SMALL_CHUNK_STEPS, kEnt = 2 * kChunk + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -529,11 +591,13 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
     const double h = a.piece_h[p];
     const double h2 = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
     const int n_chunks = (n + kChunk - 1) / kChunk;
-    stage(0, pos, 2 * (n < kChunk ? n : kChunk) + 1);
-    for (int c = 0; c < n_chunks; c++) {
+    const int c_lo = SLICED ? seg * ctl.chunks_per_seg : 0;
+    const int c_hi = SLICED ? ((seg + 1) * ctl.chunks_per_seg < n_chunks ? (seg + 1) * ctl.chunks_per_seg : n_chunks) : n_chunks;
+    stage(c_lo & 1, pos + 2LL * c_lo * kChunk, 2 * ((n - c_lo * kChunk) < kChunk ? (n - c_lo * kChunk) : kChunk) + 1);
+    for (int c = c_lo; c < c_hi; c++) {
       const int s0 = c * kChunk;
       const int ns = (n - s0) < kChunk ? (n - s0) : kChunk;
-      if (c + 1 < n_chunks) {
+      if (c + 1 < c_hi) {
         const int s1 = s0 + kChunk;
         stage((c + 1) & 1, pos + 2 * s1, 2 * ((n - s1) < kChunk ? (n - s1) : kChunk) + 1);
         asm volatile("cp.async.wait_group 1;");
@@ -647,7 +711,47 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a) {
     }
     pos += 2LL * n + 1;
     mask_pos += n_chunks;
-    if (a.keep[p + 1]) emit();
+    if (!SLICED || seg == ctl.nseg - 1) {
+      if (a.keep[p + 1]) emit();
+    }
+  }
+  if (!SLICED) return;
+  if (seg + 1 < ctl.nseg) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      __stcg(st_ptr + i, y0r[i]);
+      __stcg(st_ptr + D + i, y0i[i]);
+      __stcg(st_ptr + 2 * D + i, y1r[i]);
+      __stcg(st_ptr + 3 * D + i, y1i[i]);
+    }
+    __stcg(st_ptr + 4 * D, env0.re);
+    __stcg(st_ptr + 4 * D + 1, env0.im);
+    __stcg(st_ptr + 4 * D + 2, env1.re);
+    __stcg(st_ptr + 4 * D + 3, env1.im);
+    __stcg(st_ptr + 4 * D + 4, (double)cur_idx);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {  // the next segment of this block of trajectories goes to the worker that has waited longest
+      const unsigned t = atomicAdd(ctl.tail, 1u);
+      ((volatile int*)ctl.slot)[t] = job * ctl.nseg + seg + 1;
+      __threadfence();
+      ((volatile unsigned*)ctl.flag)[t] = 1u;
+    }
+  }
+  __syncthreads();
+ }
+}
+
+// queue set-up of the sliced kernel: segment 0 of every job is ready
+__global__ void sv_small2_slice_init_kernel(SliceCtl ctl) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    *ctl.head = 0u;
+    *ctl.tail = (unsigned)ctl.n_jobs;
+  }
+  if (i < ctl.total) {
+    ctl.slot[i] = i < (unsigned)ctl.n_jobs ? (int)i * ctl.nseg : -1;
+    ctl.flag[i] = i < (unsigned)ctl.n_jobs ? 1u : 0u;
   }
 }
 
@@ -810,6 +914,7 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     }
     m->tab_NT = NT;
     m->tab_n_pieces = n_pieces;
+    m->tab_piece0_steps = g.piece_nsteps[0];
     if ((rc = m->tab_times.ensure(NT * sizeof(double)))) return rc;
     if ((rc = m->tab_idx.ensure(NT * sizeof(int)))) return rc;
     if ((rc = m->tab.ensure((size_t)NT * W * sizeof(double)))) return rc;
@@ -898,13 +1003,52 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     const long long threads = (B + 1) / 2;
     const unsigned grid = (unsigned)((threads + block - 1) / block);
     constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
+    // Time slicing (see SliceCtl): one piece, and a block count that does not divide evenly over the SMs.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const int n_steps0 = m->tab_n_pieces == 1 ? m->tab_piece0_steps : 0;
+    const int n_chunks0 = (n_steps0 + SMALL_CHUNK_STEPS - 1) / SMALL_CHUNK_STEPS;
+    const double per_sm = (double)grid / sms;
+    bool sliced = m->tab_n_pieces == 1 && grid > (unsigned)sms && n_chunks0 >= 32 && std::fabs(per_sm - std::round(per_sm)) > 0.02;
+    if (const char* env = getenv("CASQ_SMALL_SLICED")) sliced = atoi(env) != 0 && m->tab_n_pieces == 1 && n_chunks0 >= 2;
+    SliceCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    if (sliced) {
+      ctl.n_jobs = (int)grid;
+      ctl.chunks_per_seg = 4;  // measured at 1e5 points: 1 / 2 / 3 / 4 / 8 / 16 / 64 chunks: 10.48 / 9.87 / 9.81 / 9.84 / 10.00 / 10.46 / 11.46 ms (unsliced 10.29)
+      if (const char* env = getenv("CASQ_SMALL_SLICE_CHUNKS")) ctl.chunks_per_seg = std::max(1, atoi(env));
+      ctl.nseg = (n_chunks0 + ctl.chunks_per_seg - 1) / ctl.chunks_per_seg;
+      ctl.total = (unsigned)ctl.n_jobs * (unsigned)ctl.nseg;
+      const size_t o_slot = 64, o_flag = o_slot + (((size_t)ctl.total * 4 + 63) & ~(size_t)63);
+      const size_t o_state = o_flag + (((size_t)ctl.total * 4 + 63) & ~(size_t)63);
+      const size_t bytes = o_state + (size_t)ctl.n_jobs * 64 * (4 * d + 5) * sizeof(double);
+      if ((rc = m->slice_buf.ensure(bytes))) return rc;
+      unsigned char* sb = (unsigned char*)m->slice_buf.p;
+      ctl.head = (unsigned*)sb;
+      ctl.tail = (unsigned*)(sb + 32);
+      ctl.slot = (int*)(sb + o_slot);
+      ctl.flag = (unsigned*)(sb + o_flag);
+      ctl.state = (double*)(sb + o_state);
+      sv_small2_slice_init_kernel<<<(ctl.total + 255) / 256, 256, 0, st>>>(ctl);
+    }
 #define LAUNCH2(D_, T_)                                                                                                    \
   {                                                                                                                        \
     const size_t smem2 = 2 * (size_t)kEnt * Entry<D_, 1, false, false, T_>::W * sizeof(double);                            \
-    e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);       \
-    if (e == cudaSuccess) {                                                                                                \
-      sv_rk4_small2_kernel<D_, T_><<<grid, block, smem2, st>>>(a);                                                         \
-      e = cudaGetLastError();                                                                                              \
+    if (sliced) {                                                                                                          \
+      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+      int nb = 0;                                                                                                          \
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv_rk4_small2_kernel<D_, T_, true>, block, smem2); \
+      if (e == cudaSuccess) {                                                                                              \
+        const unsigned workers = (unsigned)std::max(1, nb) * (unsigned)sms; /* every resident block slot */                \
+        sv_rk4_small2_kernel<D_, T_, true><<<workers, block, smem2, st>>>(a, ctl);                                         \
+        e = cudaGetLastError();                                                                                            \
+      }                                                                                                                    \
+    } else {                                                                                                               \
+      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+      if (e == cudaSuccess) {                                                                                              \
+        sv_rk4_small2_kernel<D_, T_, false><<<grid, block, smem2, st>>>(a, ctl);                                           \
+        e = cudaGetLastError();                                                                                            \
+      }                                                                                                                    \
     }                                                                                                                      \
   }
     if (d == 2) LAUNCH2(2, true)

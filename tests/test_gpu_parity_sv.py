@@ -412,6 +412,21 @@ def test_rk4_two_per_thread_kernel_is_bit_identical_to_one_per_thread(case, monk
         samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [{k: v[idx] for k, v in p.items()}])
         _, want = O.rk4_solve(om, samples, y0[idx], span, DT / 40, te)
         assert np.abs(auto.cpu().numpy()[idx] - want).max() < TOL_STATE
+        # one piece (no t_eval): B = 1e5 takes the TIME-SLICED persistent kernel (782 blocks do not divide over 148 SMs).
+        # Sliced, unsliced and one-trajectory-per-thread runs must agree bit for bit, for two segment lengths.
+        runs = {}
+        for tag, env in (("sliced4", {"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "4"}),
+                         ("sliced7", {"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "7"}),
+                         ("unsliced", {"CASQ_SMALL_SLICED": "0"}), ("one", {"CASQ_SMALL_TRAJ_PER_THREAD": "1"}), ("default", {})):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            nm.invalidate_cache()
+            runs[tag] = engine.solve_sv_rk4(nm, slots, params, y0, span, DT / 40).clone()
+            torch.cuda.synchronize()
+            for k in env:
+                monkeypatch.delenv(k)
+        for tag in ("sliced7", "unsliced", "one", "default"):
+            assert torch.equal(runs["sliced4"], runs[tag]), (case[0], B, tag)
 
 
 def test_cfg5_dopri5_256_candidates_against_oracle_and_truth():
