@@ -252,7 +252,7 @@ def run_configs(ctx) -> dict:
         keep["U"] = engine.propagators_expm(nm2, sl3, p3, (0.0, 1024 * DT), DT)
         keep["all"] = gather_batch(keep["U"], B3 * world, dst=0)
 
-    ms = ctx["max_over_ranks"](ctx["timed"](run3, reps, warm=1))
+    ms = ctx["max_over_ranks"](ctx["timed"](run3, reps, warm=2))
     U = keep["U"]
     unit = float((U.conj().transpose(1, 2) @ U - torch.eye(9, device=dev, dtype=U.dtype)).abs().max())
     flop3 = 6.0e4 * 1024 * B3  # F_expm(9, s=2) ~ 6.0e4 flop per step (Pade-13 count; the kernel runs orders 3-9)
@@ -262,12 +262,8 @@ def run_configs(ctx) -> dict:
           "roofline": {"bound": "fp64", "achieved": flop3 / (ms * 1e-3) / 1e12, "peak": ctx["fp64_peak"], "unit": "TFLOP/s",
                        "frac": flop3 / (ms * 1e-3) / 1e12 / ctx["fp64_peak"] if ctx["fp64_peak"] else None, "traffic": None,
                        "flop_per_step_model": 6.0e4, "kernel": "propagator_expm_kernel<9>"}}
-    if ctx["cpu"]:
-        pts = [0, 1365, 2730, 4095]
-        sec, Uo = cpu_cfg3(pts)
-        r3["cpu_baseline"] = {"value": len(pts) / sec, "unit": "unitaries/s", "cores": 1, "kind": "port",
-                              "sample": f"{len(pts)} points of the grid, 1024 scipy-expm steps each"}
-        r3["max_err"] = float(np.abs(U[pts].cpu().numpy() - Uo).max())
+    pts3 = [0, 1365, 2730, 4095]
+    U3_host = U[pts3].cpu().numpy() if ctx["cpu"] else None
     res["cfg3"] = r3
     del keep, U
     # ---------------- cfg 5: 1e4 DRAG candidates per GPU, adaptive Dopri5 (atol 1e-6, rtol 1e-8, hmax dt)
@@ -284,7 +280,7 @@ def run_configs(ctx) -> dict:
                                            return_stats=True)
         keep["all"] = gather_batch(keep["r"][0][:, -1], B5 * world, dst=0)
 
-    ms = ctx["max_over_ranks"](ctx["timed"](run5, 3, warm=1))
+    ms = ctx["max_over_ranks"](ctx["timed"](run5, 5, warm=3))  # 5 ms kernel: enough warm-up for the clocks to be up
     y5, ns5, st5 = keep["r"]
     att = int(ns5[:, 0].sum())
     flop5 = 1152.0 * att  # F_step^{DP5} = 1152 flop per ATTEMPTED step, counted by the kernel
@@ -296,12 +292,8 @@ def run_configs(ctx) -> dict:
           "roofline": {"bound": "fp64", "achieved": flop5 / (ms * 1e-3) / 1e12, "peak": ctx["fp64_peak"], "unit": "TFLOP/s",
                        "frac": flop5 / (ms * 1e-3) / 1e12 / ctx["fp64_peak"] if ctx["fp64_peak"] else None, "traffic": None,
                        "flop_per_attempted_step": 1152, "kernel": "sv_dopri5_kernel<3,1>"}}
-    if ctx["cpu"]:
-        pts = np.arange(0, B5, B5 // 12)[:12]
-        sec, yo = cpu_cfg5(pts)
-        r5["cpu_baseline"] = {"value": len(pts) / sec, "unit": "trajectories/s", "cores": 1, "kind": "port",
-                              "sample": f"{len(pts)} candidates, single-point jax-odeint restatement in a Python loop"}
-        r5["max_err"] = float(np.abs(y5[torch.as_tensor(pts, device=dev), -1].cpu().numpy() - yo).max())
+    pts5 = np.arange(0, B5, B5 // 12)[:12]
+    y5_host = y5[torch.as_tensor(pts5, device=dev), -1].cpu().numpy() if ctx["cpu"] else None
     res["cfg5"] = r5
     del keep
     # ---------------- cfg 4: 5 transmons (d = 243), T1/T2 Lindblad, RK4 dt/4 (S = 1028), 128 density matrices per GPU
@@ -337,7 +329,18 @@ def run_configs(ctx) -> dict:
                        "traffic_unit": "DRAM bytes per RK4 step (4 stage launches) at B = 128, ncu; algorithmic: 7.558e6 x 128",
                        "bytes_per_step_model": 7.558e6, "peak_source": src,
                        "kernel": "lindblad_chain_tma_kernel<5,1> (4 launches per RK4 step) + lindblad_chain_coef_kernel"}}
+    # ---------------- CPU baselines last: the GPU is never left idle between the timed configs (clocks stay up)
     if ctx["cpu"]:
+        sec, Uo = cpu_cfg3(pts3)
+        r3["cpu_baseline"] = {"value": len(pts3) / sec, "unit": "unitaries/s", "cores": 1, "kind": "port",
+                              "sample": f"{len(pts3)} points of the grid, 1024 scipy-expm steps each"}
+        r3["max_err"] = float(np.abs(U3_host - Uo).max())
+        sec, yo = cpu_cfg5(pts5)
+        r5["cpu_baseline"] = {"value": len(pts5) / sec, "unit": "trajectories/s", "cores": 1, "kind": "port",
+                              "sample": f"{len(pts5)} candidates, single-point jax-odeint restatement in a Python loop"}
+        r5["max_err"] = float(np.abs(y5_host - yo).max())
+        r5["max_err_note"] = ("adaptive controller at the config's own tolerances: the method itself is 4e-5..2e-4 from a tight "
+                              "solve there; <= 1e-6 is asserted at rtol = atol = 1e-10 (tests/test_gpu_parity_sv.py)")
         n_s = 12
         sec, rho_o = cpu_cfg4(n_s)
         rho_g, _ = engine.solve_lindblad_rk4(nm5, sl4, p4[:, :, -1:].contiguous(), rho0, (0.0, n_s * DT), DT / 4, want_pops=False)
@@ -530,6 +533,13 @@ def run_ours(args) -> None:
                   "unit": "trajectories/s", "scaling": "strong"}
 
     fp64_peak = engine.fp64_fma_probe(local_rank)
+    # the other configs are timed BEFORE any CPU baseline runs, so the GPU is never idle between timed regions
+    configs = None
+    if not args.no_configs:
+        barrier()
+        configs = run_configs({"torch": torch, "dev": dev, "rank": rank, "world": world, "timed": timed,
+                               "max_over_ranks": max_over_ranks, "fp64_peak": fp64_peak,
+                               "cpu": rank == 0 and world == 1 and not args.no_cpu_baseline})
     cpu = None
     max_state_err = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -543,12 +553,6 @@ def run_ours(args) -> None:
         got = out[torch.as_tensor(idx, device=dev), 1, :].cpu().numpy()
         max_state_err = {"value": float(np.abs(got - want).max()), "points": n, "against": "oracle port (same RK4 grid)",
                          "bar": 1e-6}
-    configs = None
-    if not args.no_configs:
-        barrier()
-        configs = run_configs({"torch": torch, "dev": dev, "rank": rank, "world": world, "timed": timed,
-                               "max_over_ranks": max_over_ranks, "fp64_peak": fp64_peak,
-                               "cpu": rank == 0 and world == 1 and not args.no_cpu_baseline})
     if world > 1:
         dist.barrier()
     if rank == 0:
