@@ -438,7 +438,12 @@ def run_ours(args) -> None:
     max_dt = DT / SUBSTEPS
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     out = torch.empty((B, 2, 3), dtype=torch.complex128, device=dev)
-    from casq_b200.distributed import gather_batch, shard_bounds
+    from casq_b200.distributed import PeerResultBuffer, gather_batch, shard_bounds
+
+    # Sharded runs write their results straight into rank 0's memory (peer stores over NVLink from the kernel's epilogue)
+    peer = PeerResultBuffer((B, 2, 3), torch.complex128, dev, dst=0) if world > 1 else None
+    if peer is not None:
+        out = peer.slot
 
     def barrier():
         if world > 1:
@@ -456,8 +461,8 @@ def run_ours(args) -> None:
         """table kernel + RK4 kernel (+ the one result gather when sharded)."""
         model.invalidate_cache()
         engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
-        if world > 1:  # the one collective of the path: final states to rank 0 (the only consumer)
-            gather_batch(out[:, 1, :], B * world, dst=0)
+        if world > 1 and not os.environ.get("CASQ_BENCH_NO_GATHER"):  # the one exchange of the path: final states on rank 0
+            peer.sync()                                                # (the env knob is a diagnosis aid: pace of the slowest GPU)
 
     def timed(fn, k, warm=0):
         for _ in range(warm):
@@ -519,18 +524,20 @@ def run_ours(args) -> None:
         lo, hi = shard_bounds(B, rank, world)
         sp = sweep_params(0)
         sub_params = engine.pack_params([dict(amp=sp["amp"][lo:hi], angle=0.0, sigma=SIGMA, beta=sp["beta"][lo:hi])], device=dev)
-        sub_out = torch.empty((hi - lo, 2, 3), dtype=torch.complex128, device=dev)
+        peer_s = PeerResultBuffer((-(-B // world), 2, 3), torch.complex128, dev, dst=0)
+        sub_out = peer_s.slot[: hi - lo]
 
         def strong_step():
             model.invalidate_cache()
             engine.solve_sv_rk4(model, slots, sub_params, y0, t_span, max_dt, out=sub_out)
-            gather_batch(sub_out[:, 1, :], B, dst=0)
+            peer_s.sync()
 
         barrier()
         ms_strong = max_over_ranks(timed(strong_step, args.steps, warm=args.warmup))
         barrier()
         strong = {"global_points": B, "points_per_gpu": B // world, "ms_per_step": ms_strong, "value": B / (ms_strong * 1e-3),
                   "unit": "trajectories/s", "scaling": "strong"}
+
 
     fp64_peak = engine.fp64_fma_probe(local_rank)
     # the other configs are timed BEFORE any CPU baseline runs, so the GPU is never idle between timed regions

@@ -61,3 +61,44 @@ def test_two_rank_gloo_shard_and_gather(total):
             assert torch.equal(only0, want.real)
         else:
             assert only0 is None
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from casq_b200.distributed import PeerResultBuffer
+
+        buf = PeerResultBuffer((4, 2, 3), torch.complex128, "cpu", dst=0)
+        assert not buf.fused and buf.slot.shape == (4, 2, 3)  # CPU / gloo: the collective fallback
+        buf.slot.copy_(torch.full((4, 2, 3), complex(rank + 1, -rank), dtype=torch.complex128))
+        buf.sync()
+        q.put((rank, buf.result()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_result_buffer_falls_back_to_a_gather_without_symmetric_memory():
+    """PeerResultBuffer on CPU tensors (gloo): same interface, results in rank order on the destination rank only.  On a B200
+    box the slot is peer memory and the producing kernel's stores are the exchange (covered by bench.py --gpus N)."""
+    from casq_b200.distributed import PeerResultBuffer
+
+    single = PeerResultBuffer((3, 2), torch.float64, "cpu")
+    single.slot.fill_(2.0)
+    single.sync()
+    assert single.world == 1 and torch.equal(single.result(), torch.full((3, 2), 2.0, dtype=torch.float64))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[1] is None
+    want = torch.cat([torch.full((4, 2, 3), complex(1, 0), dtype=torch.complex128), torch.full((4, 2, 3), complex(2, -1), dtype=torch.complex128)])
+    assert torch.equal(results[0], want)
