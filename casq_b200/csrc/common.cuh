@@ -77,6 +77,10 @@ struct casq_model {
   long long tab_NT = 0;   // shape of the cached fixed-step grid (small RK4 path)
   int tab_n_pieces = 0, tab_piece0_steps = 0;
   DeviceBuf slice_buf;    // ticket queue and hand-over state of the time-sliced headline kernel
+  // pinned host staging of the small RK4 path's grid upload (pageable cudaMemcpyAsync synchronises the stream per copy)
+  void* stage_h = nullptr;
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_ev = nullptr;  // recorded after the last copy that reads stage_h
   // second stream + fork/join events of the Lindblad path (several parts of the batch in flight fill each other's grid tails)
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};

@@ -267,6 +267,8 @@ extern "C" void casq_model_destroy(casq_model* m) {
   DeviceBuf* bufs[] = {&m->tab, &m->tab_idx, &m->tab_times, &m->pieces_n, &m->pieces_h, &m->consts,
                        &m->work0, &m->work1, &m->work2, &m->work3, &m->slice_buf};
   for (DeviceBuf* b : bufs) b->release();
+  if (m->stage_h) cudaFreeHost(m->stage_h);
+  if (m->stage_ev) cudaEventDestroy(m->stage_ev);
   for (int i = 0; i < 3; i++) {
     if (m->aux_stream[i]) cudaStreamDestroy(m->aux_stream[i]);
     if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
@@ -321,6 +323,20 @@ long long casq_py_floor_divide(double a, double b) {
   return (long long)fl;
 }
 
+// The same quotient without the iterative fmod: a guess from one multiplication, corrected by the EXACT sign of the remainder
+// a - q b (one FMA; the device steppers use the same rule, dopri5_common.cuh).  Only a remainder that rounds to exactly b is
+// ambiguous: that case takes the reference path above.
+static inline long long floor_divide_fast(double a, double b, double inv_b) {
+  double q = std::floor(a * inv_b);
+  const double r = std::fma(-q, b, a);
+  if (r == b || !(b > 0)) return casq_py_floor_divide(a, b);
+  if (r < 0.0)
+    q -= 1.0;
+  else if (r > b)
+    q += 1.0;
+  return (long long)q;
+}
+
 int casq_build_time_grid(double t0, double t1, double max_dt, int T, const double* t_eval, double dt,
                          int n_total, TimeGrid* g) {
   if (!(max_dt > 0)) CASQ_FAIL(CASQ_ERR_INVALID, "fixed-step solve needs max_dt > 0");
@@ -354,6 +370,11 @@ int casq_build_time_grid(double t0, double t1, double max_dt, int T, const doubl
   g->piece_h.assign(np, 0.0);
   g->times.clear();
   g->sample_idx.clear();
+  {
+    size_t total = 0;
+    for (int p = 0; p < np; p++) total += 2 * (size_t)std::min(1e9, std::fabs((pts[p + 1] - pts[p]) / max_dt) + 2.0) + 1;
+    g->times.reserve(total);
+  }
   for (int p = 0; p < np; p++) {
     double delta = pts[p + 1] - pts[p];
     long long n = (long long)std::fabs(delta / max_dt);
@@ -375,8 +396,9 @@ int casq_build_time_grid(double t0, double t1, double max_dt, int T, const doubl
     g->times.push_back(t);
   }
   g->sample_idx.resize(g->times.size());
+  const double inv_dt = 1.0 / dt;
   for (size_t i = 0; i < g->times.size(); i++) {
-    long long q = casq_py_floor_divide(g->times[i], dt);
+    long long q = floor_divide_fast(g->times[i], dt, inv_dt);
     if (q < -1) q = -1;
     if (q > n_total) q = n_total;
     g->sample_idx[i] = (int)q;

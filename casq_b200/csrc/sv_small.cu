@@ -922,12 +922,36 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     if ((rc = m->pieces_h.ensure(n_pieces * sizeof(double)))) return rc;
     if ((rc = m->consts.ensure(keep.size()))) return rc;
     if ((rc = m->work2.ensure(masks.size() * sizeof(unsigned)))) return rc;
-    CASQ_CUDA(cudaMemcpyAsync(m->work2.p, masks.data(), masks.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    CASQ_CUDA(cudaMemcpyAsync(m->tab_times.p, g.times.data(), NT * sizeof(double), cudaMemcpyHostToDevice, st));
-    CASQ_CUDA(cudaMemcpyAsync(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), cudaMemcpyHostToDevice, st));
-    CASQ_CUDA(cudaMemcpyAsync(m->pieces_n.p, g.piece_nsteps.data(), n_pieces * sizeof(int), cudaMemcpyHostToDevice, st));
-    CASQ_CUDA(cudaMemcpyAsync(m->pieces_h.p, g.piece_h.data(), n_pieces * sizeof(double), cudaMemcpyHostToDevice, st));
-    CASQ_CUDA(cudaMemcpyAsync(m->consts.p, keep.data(), keep.size(), cudaMemcpyHostToDevice, st));
+    {
+      // one pinned staging buffer for the six uploads: truly asynchronous copies, queued back to back
+      auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+      const size_t b_masks = up8(masks.size() * sizeof(unsigned)), b_times = NT * sizeof(double), b_idx = up8(NT * sizeof(int));
+      const size_t b_pn = up8(n_pieces * sizeof(int)), b_ph = n_pieces * sizeof(double), b_keep = up8(keep.size());
+      const size_t need = b_masks + b_times + b_idx + b_pn + b_ph + b_keep;
+      if (m->stage_ev) CASQ_CUDA(cudaEventSynchronize(m->stage_ev));  // the previous upload has left the staging buffer
+      if (need > m->stage_bytes) {
+        if (m->stage_h) cudaFreeHost(m->stage_h);
+        m->stage_h = nullptr;
+        m->stage_bytes = 0;
+        CASQ_CUDA(cudaHostAlloc(&m->stage_h, need + need / 2, cudaHostAllocDefault));
+        m->stage_bytes = need + need / 2;
+      }
+      if (!m->stage_ev) CASQ_CUDA(cudaEventCreateWithFlags(&m->stage_ev, cudaEventDisableTiming));
+      unsigned char* hp = (unsigned char*)m->stage_h;
+      auto put = [&](void* dst, const void* src, size_t bytes, size_t padded) -> cudaError_t {
+        memcpy(hp, src, bytes);
+        cudaError_t e2 = cudaMemcpyAsync(dst, hp, bytes, cudaMemcpyHostToDevice, st);
+        hp += padded;
+        return e2;
+      };
+      CASQ_CUDA(put(m->work2.p, masks.data(), masks.size() * sizeof(unsigned), b_masks));
+      CASQ_CUDA(put(m->tab_times.p, g.times.data(), NT * sizeof(double), b_times));
+      CASQ_CUDA(put(m->tab_idx.p, g.sample_idx.data(), NT * sizeof(int), b_idx));
+      CASQ_CUDA(put(m->pieces_n.p, g.piece_nsteps.data(), n_pieces * sizeof(int), b_pn));
+      CASQ_CUDA(put(m->pieces_h.p, g.piece_h.data(), n_pieces * sizeof(double), b_ph));
+      CASQ_CUDA(put(m->consts.p, keep.data(), keep.size(), b_keep));
+      CASQ_CUDA(cudaEventRecord(m->stage_ev, st));
+    }
     TableArgs ta;
     memset(&ta, 0, sizeof(ta));
     ta.times = (const double*)m->tab_times.p;
