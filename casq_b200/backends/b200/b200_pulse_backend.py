@@ -9,6 +9,7 @@ sweep API; a sweep there is a Python loop of ``solve`` calls).
 """
 from __future__ import annotations
 
+import logging
 from dataclasses import dataclass
 from datetime import datetime
 from typing import Any, Optional, Sequence, Union
@@ -27,6 +28,7 @@ from ...pulse import Play, Schedule, SetFrequency, SetPhase, ShiftFrequency, Shi
 from ...quantum_info import DensityMatrix, Statevector, populations_by_qubit
 from ..pulse_backend import PulseBackend
 
+_log = logging.getLogger("casq_b200")
 _FIXED = ("RK4", "jax_RK4")
 _SCIPY = ("BDF", "DOP853", "Radau", "RK23", "RK45")
 
@@ -207,6 +209,9 @@ class B200PulseBackend(PulseBackend):
                 raise CasqError(f"Method '{method}' is a fixed-step solver and needs run_options['max_dt'].")
             raw = engine.solve_sv_rk4(model, slots, params_dev, y0, t_span, options["max_dt"], t_eval)
         elif method == "jax_odeint" or method in _SCIPY:
+            if method in _SCIPY and "rtol" not in options and "atol" not in options:
+                _log.warning("ODE method '%s' runs on the device Dopri5 with rtol = atol = 1.4e-8; casq's scipy path would run at "
+                             "scipy's defaults (rtol 1e-3, atol 1e-6). Pass run_options={'rtol':..., 'atol':...} to choose.", method)
             # scipy-named adaptive methods run on the device Dopri5 as well.  casq passes no tolerances, so the
             # reference runs them at scipy's rtol=1e-3 (SURVEY §3.1 "accuracy trap"); here an unset tolerance
             # means 1.4e-8 (the jax_odeint default), i.e. closer to the true solution than the reference.
