@@ -26,8 +26,8 @@ __device__ __forceinline__ int dev_sample_index_fast(double t, double dt, double
   const double r = fma(-q, dt, t);
   if (r == dt) return dev_sample_index(t, dt, n_total);
   q += (r < 0.0) ? -1.0 : (r > dt ? 1.0 : 0.0);
-  q = fmin(fmax(q, -1.0), (double)n_total);
-  return (int)q;
+  // the conversion saturates, so the clip can be done on the integer (two IMNMX instead of two emulated fp64 min/max)
+  return min(max(__double2int_rz(q), -1), n_total);
 }
 
 // Branch-free fp64 sincos for |x| < 1e5 (phases reach ~2e3 rad here): two-FMA Cody-Waite reduction by pi/2 and the
@@ -60,7 +60,25 @@ __device__ __forceinline__ void dp_sincos_fast(double x, double* sn, double* cs)
   const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
   const int q = (int)n;
   const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
-  *sn = (q & 2) ? -s0 : s0;
-  *cs = ((q + 1) & 2) ? -c0 : c0;
+  // quadrant signs flipped in the sign bit directly (one LOP3 each; the ?: form cost a negate and two selects)
+  *sn = __hiloint2double(__double2hiint(s0) ^ ((q & 2) << 30), __double2loint(s0));
+  *cs = __hiloint2double(__double2hiint(c0) ^ (((q + 1) & 2) << 30), __double2loint(c0));
 }
 
+
+// Step-size factor of the controller, min(10, max(0.9 ratio^(-1/5), ratio < 1 ? 1 : 0.2)), from the MEAN SQUARE error
+// ratio m = ratio^2 (so the caller needs no square root: ratio <= 1 iff m <= 1).  m^(-1/10) comes from an fp32 seed and
+// two Newton steps on x^-10 = m (x <- x (1.1 - 0.1 m x^10), error 5.5 e^2 per step: 1e-5 -> 6e-10 -> 2e-18), ~25
+// instructions where exp2(-0.2 log2(ratio)) took 155 and sat on the critical path of every step.  Outside [1e-14, 1e8]
+// the result is clipped to 10 or 0.2 anyway, so m is clamped first (which also covers m = 0 and keeps the seed finite).
+__device__ __forceinline__ double dp_step_factor(double m) {
+  const double dfac = m < 1.0 ? 1.0 : 0.2;
+  const double r = (m == m) ? fmin(fmax(m, 1e-14), 1e8) : 1e8;  // NaN error estimate: shrink like a huge one
+  double x = (double)exp2f(-0.1f * __log2f((float)r));
+#pragma unroll
+  for (int it = 0; it < 2; it++) {
+    const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+    x = x * fma(-0.1 * r, x8 * x2, 1.1);
+  }
+  return fmin(10.0, fmax(0.9 * x, dfac));
+}

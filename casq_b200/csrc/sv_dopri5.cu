@@ -11,6 +11,7 @@
 //
 // Unlike the fixed-step kernel the time points differ per trajectory, so carrier and Bohr phases are
 // evaluated with fp64 sincos per stage (phases reach ~2e3 rad: fp32 is not an option).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -43,6 +44,9 @@ struct Dopri5Args {
   int has_diag;
   double two_pi_nu[DP_MAXK];
   double bohr[DP_MAXE];
+  double freq_max;                       // max |phase_freq|: |t| freq_max < DP_TRIG_MAX selects the branch-free sincos
+  double phase_freq[DP_MAXK + DP_MAXE];  // the phases one stage needs, in order: carriers, then the Bohr frequency of every
+                                         // element the kernel variant carries (ladder elements only for TRI; 0 where masked)
   double Sr[DP_MAXE], Si[DP_MAXE];
   double Pr[DP_MAXK][DP_MAXE], Pi[DP_MAXK][DP_MAXE];
   double Nr[DP_MAXK][DP_MAXE], Ni[DP_MAXK][DP_MAXE];
@@ -58,37 +62,54 @@ struct Dopri5Args {
 
 // Everything of the right-hand side that depends on t only: h_d[i] (real diagonal) and the upper-triangle elements
 // h[e] = (S + sum_k z_k P_k + conj(z_k) N_k)[i,j] e^{i(e_i - e_j)t} of the frame-rotated Hamiltonian.
+// TRI: only the ladder elements (i, i+1) exist (a transmon drive a + a^dagger in its own eigenbasis) -- D-1 Bohr phases
+// instead of D(D-1)/2, and the apply skips the rest statically.
 template <int D>
 struct DpCoef {
   double hd[D];
   double hr[D * (D - 1) / 2], hi[D * (D - 1) / 2];
 };
 
-template <int D, int KA>
-__device__ __forceinline__ void dp_coef(const Dopri5Args& a, long long b, double t, DpCoef<D>& cf) {
-  constexpr int E = D * (D - 1) / 2;
+template <int D>
+__host__ __device__ constexpr int dp_tri_e(int i) {  // index of (i, i+1) in the row-major upper-triangle enumeration
+  return i * (2 * D - i - 1) / 2;
+}
+template <int D, int KA, bool TRI>
+struct DpShape {
+  static constexpr int E = D * (D - 1) / 2;
+  static constexpr int EP = TRI ? D - 1 : E;  // elements carried
+  static constexpr int NPH = KA + EP;         // phases per stage time
+};
+
+// sin / cos of N phases; `fast`: every argument is inside the range of the branch-free routine (the caller tests
+// |t| max|freq| once instead of reducing over the arguments)
+template <int N>
+__device__ __forceinline__ void dp_sincos_n(bool fast, const double* x, double* sn, double* cs) {
+  if (fast) {
+#pragma unroll
+    for (int n = 0; n < N; n++) dp_sincos_fast(x[n], &sn[n], &cs[n]);
+  } else {
+#pragma unroll
+    for (int n = 0; n < N; n++) sincos(x[n], &sn[n], &cs[n]);
+  }
+}
+__device__ __forceinline__ bool dp_fast_range(const Dopri5Args& a, double t) { return fabs(t) * a.freq_max < DP_TRIG_MAX; }
+
+// envelope samples of the driven channels at time t (zero outside the schedule)
+template <int KA>
+__device__ __forceinline__ void dp_env(const Dopri5Args& a, long long b, double t, double2* env) {
   const int gidx = dev_sample_index_fast(t, a.dt_sample, a.inv_dt_sample, a.n_total);
   const bool inside = gidx >= 0 && gidx < a.n_total;
-  double2 env[KA];
 #pragma unroll
   for (int k = 0; k < KA; k++)
     env[k] = inside ? __ldg(a.env_tab + ((long long)k * a.n_total + gidx) * a.B + b) : make_double2(0.0, 0.0);
-  // phases: carriers first, then the Bohr frequencies of the populated elements
-  double x[KA + E], sn[KA + E], cs[KA + E];
-  double xmax = 0.0;
-#pragma unroll
-  for (int k = 0; k < KA; k++) x[k] = a.two_pi_nu[k] * t;
-#pragma unroll
-  for (int e = 0; e < E; e++) x[KA + e] = (a.emask & (1u << e)) ? a.bohr[e] * t : 0.0;
-#pragma unroll
-  for (int n = 0; n < KA + E; n++) xmax = fmax(xmax, fabs(x[n]));
-  if (xmax < DP_TRIG_MAX) {
-#pragma unroll
-    for (int n = 0; n < KA + E; n++) dp_sincos_fast(x[n], &sn[n], &cs[n]);
-  } else {
-#pragma unroll
-    for (int n = 0; n < KA + E; n++) sincos(x[n], &sn[n], &cs[n]);
-  }
+}
+
+// The coefficients at one time from its envelope samples and the NPH sines / cosines of a.phase_freq[n] * t.
+template <int D, int KA, bool TRI>
+__device__ __forceinline__ void dp_build(const Dopri5Args& a, const double2* env, const double* sn, const double* cs,
+                                         DpCoef<D>& cf) {
+  constexpr int EP = DpShape<D, KA, TRI>::EP;
   double zr[KA], zi[KA];
 #pragma unroll
   for (int k = 0; k < KA; k++) {
@@ -106,7 +127,8 @@ __device__ __forceinline__ void dp_coef(const Dopri5Args& a, long long b, double
     cf.hd[i] = h;
   }
 #pragma unroll
-  for (int e = 0; e < E; e++) {
+  for (int p = 0; p < EP; p++) {
+    const int e = TRI ? dp_tri_e<D>(p) : p;
     double gr = a.Sr[e], gi = a.Si[e];
 #pragma unroll
     for (int k = 0; k < KA; k++) {
@@ -114,13 +136,23 @@ __device__ __forceinline__ void dp_coef(const Dopri5Args& a, long long b, double
       gr += zr[k] * (a.Pr[k][e] + a.Nr[k][e]) - zi[k] * (a.Pi[k][e] - a.Ni[k][e]);
       gi += zr[k] * (a.Pi[k][e] + a.Ni[k][e]) + zi[k] * (a.Pr[k][e] - a.Nr[k][e]);
     }
-    cf.hr[e] = gr * cs[KA + e] - gi * sn[KA + e];
-    cf.hi[e] = gr * sn[KA + e] + gi * cs[KA + e];
+    cf.hr[e] = gr * cs[KA + p] - gi * sn[KA + p];
+    cf.hi[e] = gr * sn[KA + p] + gi * cs[KA + p];
   }
 }
 
+template <int D, int KA, bool TRI>
+__device__ __forceinline__ void dp_coef(const Dopri5Args& a, const double2* env, double t, DpCoef<D>& cf) {
+  constexpr int NPH = DpShape<D, KA, TRI>::NPH;
+  double x[NPH], sn[NPH], cs[NPH];
+#pragma unroll
+  for (int n = 0; n < NPH; n++) x[n] = a.phase_freq[n] * t;
+  dp_sincos_n<NPH>(dp_fast_range(a, t), x, sn, cs);
+  dp_build<D, KA, TRI>(a, env, sn, cs, cf);
+}
+
 // k = -i H y
-template <int D>
+template <int D, bool TRI>
 __device__ __forceinline__ void dp_apply(unsigned emask, const DpCoef<D>& cf, const double* yr, const double* yi, double* kr,
                                          double* ki) {
   double wr[D], wi[D];
@@ -134,7 +166,7 @@ __device__ __forceinline__ void dp_apply(unsigned emask, const DpCoef<D>& cf, co
   for (int i = 0; i < D; i++) {
 #pragma unroll
     for (int j = i + 1; j < D; j++) {
-      if (emask & (1u << e)) {
+      if (TRI ? (j == i + 1) : ((emask & (1u << e)) != 0)) {
         const double hr = cf.hr[e], hi = cf.hi[e];
         wr[i] += hr * yr[j] - hi * yi[j];
         wi[i] += hr * yi[j] + hi * yr[j];
@@ -151,12 +183,14 @@ __device__ __forceinline__ void dp_apply(unsigned emask, const DpCoef<D>& cf, co
   }
 }
 
-template <int D, int KA>
+template <int D, int KA, bool TRI>
 __device__ __forceinline__ void dp_rhs(const Dopri5Args& a, long long b, double t, const double* yr, const double* yi,
                                        double* kr, double* ki) {
   DpCoef<D> cf;
-  dp_coef<D, KA>(a, b, t, cf);
-  dp_apply<D>(a.emask, cf, yr, yi, kr, ki);
+  double2 env[KA];
+  dp_env<KA>(a, b, t, env);
+  dp_coef<D, KA, TRI>(a, env, t, cf);
+  dp_apply<D, TRI>(a.emask, cf, yr, yi, kr, ki);
 }
 
 __constant__ double DP_ALPHA[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
@@ -173,10 +207,20 @@ __constant__ double DP_CMID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 512522929
                                   -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
                                   -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
 
-template <int D, int KA>
-__global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.B) return;
+// L lanes per trajectory (1, 2 or 4).  At the optimizer's batch sizes (1e4 candidates = 313 warps on 592 schedulers) the
+// kernel is bound by the latency of ONE warp's instruction stream, a third of which is the 5 x NPH sin/cos pairs of a
+// step.  With L > 1 the lanes of a trajectory split those evaluations (all five stage times are known when the step
+// starts) and exchange the results by shuffle; everything else is computed redundantly, in lock step, by every lane of
+// the group, so the results are the L = 1 results bit for bit.  The host uses L > 1 for small batches only (see the launch).
+template <int D, int KA, int L, bool TRI>
+__global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dopri5Args a) {
+  constexpr int NPH = DpShape<D, KA, TRI>::NPH;
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  if (b >= a.B) return;  // whole groups leave together
+  const int gl = threadIdx.x & (L - 1);
+  const int gbase = (threadIdx.x & 31) & ~(L - 1);
+  const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << gbase;
+  (void)gmask;
   double yr[D], yi[D];
   {
     const double* src = a.y0 + (a.y0_batched ? b * 2 * D : 0);
@@ -198,6 +242,8 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
   int out_slot = 0;
   auto emit = [&](const double* vr, const double* vi) {
     double* o = outp + (long long)out_slot * 2 * D;
+    out_slot++;
+    if (gl != 0) return;
 #pragma unroll
     for (int i = 0; i < D; i++) {
       double sr = 0, si = 0;
@@ -211,14 +257,13 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       o[2 * i] = sr;
       o[2 * i + 1] = si;
     }
-    out_slot++;
   };
   if (a.keep[0]) emit(yr, yi);
 
   double t = a.tpts[0];
   // k[0] = f(y0, t0)
   double kr[7][D], ki[7][D];
-  dp_rhs<D, KA>(a, b, t, yr, yi, kr[0], ki[0]);
+  dp_rhs<D, KA, TRI>(a, b, t, yr, yi, kr[0], ki[0]);
 
   // ---- initial step size (Hairer, Norsett, Wanner II.4; order 4)
   double dt;
@@ -240,7 +285,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       tr[i] = yr[i] + h0 * kr[0][i];
       ti[i] = yi[i] + h0 * ki[0][i];
     }
-    dp_rhs<D, KA>(a, b, t + h0, tr, ti, fr, fi);
+    dp_rhs<D, KA, TRI>(a, b, t + h0, tr, ti, fr, fi);
     double d2 = 0;
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -273,27 +318,84 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       break;
     }
     // ---- one attempted step.  The t-only part of the six new stages (five distinct times: stages 5 and 6 are both
-    // at t + dt) is computed first in a ROLLED loop: one copy of the index / table / sincos code instead of six keeps
-    // the step inside the instruction cache (the fully unrolled step spent 25 % of its cycles on instruction fetch
-    // with one warp per scheduler), and the five sets wait in local memory.
-    DpCoef<D> cfs[5];
+    // at t + dt) does not depend on the state.
+    if constexpr (L == 1) {
+      // computed first in a ROLLED loop: one copy of the index / table / sincos code instead of six keeps the step
+      // inside the instruction cache (the fully unrolled step spent 25 % of its cycles on instruction fetch with one
+      // warp per scheduler), and the five sets wait in local memory.
+      // The envelope look-up of stage s + 1 is issued before the sin/cos work of stage s, which hides its latency (it
+      // was 14 % of all stall samples when each iteration started with its own look-up).
+      DpCoef<D> cfs[5];
+      double2 env_next[KA];
+      dp_env<KA>(a, b, fma(dt, DP_ALPHA[0], t), env_next);
 #pragma unroll 1
-    for (int s = 0; s < 5; s++) dp_coef<D, KA>(a, b, t + dt * DP_ALPHA[s], cfs[s]);
+      for (int s = 0; s < 5; s++) {
+        double2 env[KA];
 #pragma unroll
-    for (int s = 1; s < 7; s++) {
-      double tr[D], ti[D];
-#pragma unroll
-      for (int i = 0; i < D; i++) {
-        double ar = 0, ai = 0;
-#pragma unroll
-        for (int q = 0; q < s; q++) {
-          ar += DP_BETA[s - 1][q] * kr[q][i];
-          ai += DP_BETA[s - 1][q] * ki[q][i];
-        }
-        tr[i] = yr[i] + dt * ar;
-        ti[i] = yi[i] + dt * ai;
+        for (int k = 0; k < KA; k++) env[k] = env_next[k];
+        if (s < 4) dp_env<KA>(a, b, fma(dt, DP_ALPHA[s + 1], t), env_next);
+        dp_coef<D, KA, TRI>(a, env, fma(dt, DP_ALPHA[s], t), cfs[s]);
       }
-      dp_apply<D>(a.emask, cfs[s < 6 ? s - 1 : 4], tr, ti, kr[s], ki[s]);
+#pragma unroll
+      for (int s = 1; s < 7; s++) {
+        double tr[D], ti[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double ar = 0, ai = 0;
+#pragma unroll
+          for (int q = 0; q < s; q++) {
+            ar += DP_BETA[s - 1][q] * kr[q][i];
+            ai += DP_BETA[s - 1][q] * ki[q][i];
+          }
+          tr[i] = yr[i] + dt * ar;
+          ti[i] = yi[i] + dt * ai;
+        }
+        dp_apply<D, TRI>(a.emask, cfs[s < 6 ? s - 1 : 4], tr, ti, kr[s], ki[s]);
+      }
+    } else {
+      // the 5 x NPH sin/cos pairs of the step, dealt round-robin over the L lanes of the trajectory
+      constexpr int NU = 5 * NPH, UPL = (NU + L - 1) / L;
+      double usn[UPL], ucs[UPL];
+      {
+        double ux[UPL];
+#pragma unroll
+        for (int q = 0; q < UPL; q++) {
+          int u = q * L + gl;
+          u = u < NU ? u : NU - 1;
+          const int s = u / NPH, n = u - s * NPH;
+          ux[q] = a.phase_freq[n] * fma(dt, DP_ALPHA[s], t);
+        }
+        dp_sincos_n<UPL>(dp_fast_range(a, t) && dp_fast_range(a, t + dt), ux, usn, ucs);
+      }
+      DpCoef<D> cf;
+#pragma unroll
+      for (int s = 1; s < 7; s++) {
+        if (s < 6) {
+          double sn[NPH], cs[NPH];
+#pragma unroll
+          for (int n = 0; n < NPH; n++) {
+            const int u = (s - 1) * NPH + n;
+            sn[n] = __shfl_sync(gmask, usn[u / L], gbase + (u % L));
+            cs[n] = __shfl_sync(gmask, ucs[u / L], gbase + (u % L));
+          }
+          double2 env[KA];
+          dp_env<KA>(a, b, fma(dt, DP_ALPHA[s - 1], t), env);
+          dp_build<D, KA, TRI>(a, env, sn, cs, cf);
+        }
+        double tr[D], ti[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double ar = 0, ai = 0;
+#pragma unroll
+          for (int q = 0; q < s; q++) {
+            ar += DP_BETA[s - 1][q] * kr[q][i];
+            ai += DP_BETA[s - 1][q] * ki[q][i];
+          }
+          tr[i] = yr[i] + dt * ar;
+          ti[i] = yi[i] + dt * ai;
+        }
+        dp_apply<D, TRI>(a.emask, cf, tr, ti, kr[s], ki[s]);
+      }
     }
     double y1r[D], y1i[D];
     double ratio = 0;
@@ -315,15 +417,8 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
       const double tol = a.atol + a.rtol * sqrt(fmax(yr[i] * yr[i] + yi[i] * yi[i], y1r[i] * y1r[i] + y1i[i] * y1i[i]));
       ratio += (er * er + ei * ei) / (tol * tol);
     }
-    ratio = sqrt(ratio / D);
-    double new_dt;
-    if (ratio == 0.0) {
-      new_dt = dt * 10.0;
-    } else {
-      const double dfac = ratio < 1.0 ? 1.0 : 0.2;
-      // ratio^(-1/5) as exp2(-0.2 log2 ratio): the general pow() costs ~250 instructions on the per-step critical path
-      new_dt = dt * fmin(10.0, fmax(exp2(-0.2 * log2(ratio)) * 0.9, dfac));
-    }
+    ratio *= 1.0 / D;  // MEAN SQUARE error ratio from here on: accept iff <= 1 (dp_step_factor)
+    double new_dt = dt * dp_step_factor(ratio);
     new_dt = fmin(fmax(new_dt, 0.0), a.hmax);
     n_att++;
     i_target++;
@@ -386,6 +481,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
     for (; next < a.T; next++)
       if (a.keep[next]) emit(nanv, nanv);
   }
+  if (gl != 0) return;
   if (a.nsteps) {
     a.nsteps[2 * b] = n_att;
     a.nsteps[2 * b + 1] = n_acc;
@@ -518,6 +614,27 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     }
   }
   a.identityU = m->U_is_identity ? 1 : 0;
+  // ladder-only models take the TRI variants (D = 2 has nothing else)
+  unsigned ladder = 0;
+  for (int i = 0; i + 1 < d; i++) ladder |= 1u << (i * (2 * d - i - 1) / 2);
+  const bool tri = (a.emask & ~ladder) == 0;
+  {
+    int n = 0;
+    for (int k = 0; k < KA; k++) a.phase_freq[n++] = a.two_pi_nu[k];
+    for (int k = 0; k < KA; k++) a.freq_max = std::max(a.freq_max, std::fabs(a.two_pi_nu[k]));
+    for (int e2 = 0; e2 < d * (d - 1) / 2; e2++) a.freq_max = std::max(a.freq_max, std::fabs(a.bohr[e2]));
+    const int E = d * (d - 1) / 2;
+    for (int e2 = 0; e2 < E; e2++) {
+      if (tri && !(ladder & (1u << e2))) continue;
+      a.phase_freq[n++] = (a.emask & (1u << e2)) ? a.bohr[e2] : 0.0;
+    }
+  }
+  int lanes_forced = 0;
+  if (const char* ev = getenv("CASQ_DOPRI5_LANES")) lanes_forced = atoi(ev);
+  if (lanes_forced != 0 && lanes_forced != 1 && lanes_forced != 2 && lanes_forced != 4)
+    CASQ_FAIL(CASQ_ERR_INVALID, "CASQ_DOPRI5_LANES must be 1, 2 or 4");
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   // the batch is walked in windows that bound the envelope table (one window up to 2.6e5 points at cfg 5's 257 samples)
   const long long Bw = casq_env_table_window(KA, n_total, B);
   if ((rc = m->work2.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
@@ -531,13 +648,27 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     a.out = out_dev + b0 * (long long)T * 2 * d;
     a.nsteps = nsteps_dev ? (long long*)nsteps_dev + 2 * b0 : nullptr;
     a.status = status_dev ? status_dev + b0 : nullptr;
-    const unsigned grid = (unsigned)((Bc + block - 1) / block);
-#define LAUNCH(D_, K_)                                        \
-  if (d == D_ && KA == K_) {                                  \
-    sv_dopri5_kernel<D_, K_><<<grid, block, 0, st>>>(a);      \
+    bool launched = false;
+    // lanes per trajectory: more than one only while every warp still has a scheduler to itself (4 per SM); beyond that
+    // the redundant work of the extra lanes costs more than the shorter instruction stream saves (B = 1e4 on B200:
+    // 4.8 / 5.3 / 6.0 ms with 1 / 2 / 4 lanes; B = 3e3: 4.8 / 4.6 / 4.3 ms)
+#define LAUNCH_L(D_, K_, L_, T_)                                                                                         \
+  if (!launched && (lanes_forced == 0 || lanes_forced == L_)) {                                                         \
+    const long long grid = (Bc * L_ + block - 1) / block;                                                               \
+    if (L_ == 1 || lanes_forced == L_ || grid * (block / 32) <= 4LL * n_sm) {                                           \
+      sv_dopri5_kernel<D_, K_, L_, T_><<<(unsigned)grid, block, 0, st>>>(a);                                            \
+      launched = true;                                                                                                  \
+    }                                                                                                                   \
   }
-    LAUNCH(2, 1) LAUNCH(2, 2) LAUNCH(3, 1) LAUNCH(3, 2) LAUNCH(4, 1) LAUNCH(4, 2)
+#define LAUNCH(D_, K_, T_)                                                                                               \
+  if (d == D_ && KA == K_ && tri == T_) {                                                                               \
+    LAUNCH_L(D_, K_, 4, T_) LAUNCH_L(D_, K_, 2, T_) LAUNCH_L(D_, K_, 1, T_)                                             \
+  }
+    LAUNCH(2, 1, true) LAUNCH(2, 2, true) LAUNCH(3, 1, true) LAUNCH(3, 2, true) LAUNCH(4, 1, true) LAUNCH(4, 2, true)
+    LAUNCH(3, 1, false) LAUNCH(3, 2, false) LAUNCH(4, 1, false) LAUNCH(4, 2, false)
 #undef LAUNCH
+#undef LAUNCH_L
+    if (!launched) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: no kernel variant for dim %d, %d channels", d, KA);
   }
   CASQ_CUDA(cudaGetLastError());
   return CASQ_OK;

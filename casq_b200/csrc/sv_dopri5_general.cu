@@ -313,15 +313,8 @@ __global__ void __launch_bounds__(32 * DG_WARPS) sv_dopri5_general_kernel(const 
       const double tol = a.atol + a.rtol * fmax(hypot(yr[r], yi[r]), hypot(y1r[r], y1i[r]));
       if (own[r]) ratio += (er * er + ei * ei) / (tol * tol);
     }
-    ratio = sqrt(dg_warp_sum(ratio) / d);
-    double new_dt;
-    if (ratio == 0.0) {
-      new_dt = dt * 10.0;
-    } else {
-      const double dfac = ratio < 1.0 ? 1.0 : 0.2;
-      // ratio^(-1/5) as exp2(-0.2 log2 ratio): the general pow() costs ~250 instructions on the per-step critical path
-      new_dt = dt * fmin(10.0, fmax(exp2(-0.2 * log2(ratio)) * 0.9, dfac));
-    }
+    ratio = dg_warp_sum(ratio) / d;  // MEAN SQUARE error ratio from here on: accept iff <= 1 (dp_step_factor)
+    double new_dt = dt * dp_step_factor(ratio);
     new_dt = fmin(fmax(new_dt, 0.0), a.hmax);
     n_att++;
     i_target++;
