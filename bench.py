@@ -291,7 +291,7 @@ def run_configs(ctx) -> dict:
           "best_infidelity_1_minus_P1": float((1 - pops[:, -1, 1]).min()),
           "roofline": {"bound": "fp64", "achieved": flop5 / (ms * 1e-3) / 1e12, "peak": ctx["fp64_peak"], "unit": "TFLOP/s",
                        "frac": flop5 / (ms * 1e-3) / 1e12 / ctx["fp64_peak"] if ctx["fp64_peak"] else None, "traffic": None,
-                       "flop_per_attempted_step": 1152, "kernel": "sv_dopri5_kernel<3,1>"}}
+                       "flop_per_attempted_step": 1152, "kernel": "sv_dopri5_kernel<3,1,TRI>"}}
     pts5 = np.arange(0, B5, B5 // 12)[:12]
     y5_host = y5[torch.as_tensor(pts5, device=dev), -1].cpu().numpy() if ctx["cpu"] else None
     res["cfg5"] = r5

@@ -82,3 +82,22 @@ __device__ __forceinline__ double dp_step_factor(double m) {
   }
   return fmin(10.0, fmax(0.9 * x, dfac));
 }
+
+// (er^2 + ei^2) / tol^2 with tol = atol + rtol sqrt(a), a = max(|y0|^2, |y1|^2): the error-ratio term of one component.
+// The IEEE sqrt and division (with their special-case branches) were ~50 instructions per component on the critical
+// path of every step; here 1/sqrt(a) and 1/tol come from the hardware seeds (2^-20) and two Newton steps each, accurate to
+// 1-2 ulp -- an error estimate needs no more.  tol >= atol > 0 always; a = 0 (or subnormal) gives sqrt = 0.
+__device__ __forceinline__ double dp_err_term(double e2, double a, double atol, double rtol) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double ha = 0.5 * a;
+  y = y * fma(-ha * y, y, 1.5);
+  y = y * fma(-ha * y, y, 1.5);
+  const double s = a > 1e-290 ? a * y : 0.0;
+  const double tol = fma(rtol, s, atol);
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(tol));
+  x = fma(x, fma(-tol, x, 1.0), x);
+  x = fma(x, fma(-tol, x, 1.0), x);
+  return e2 * (x * x);
+}

@@ -207,20 +207,14 @@ __constant__ double DP_CMID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 512522929
                                   -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
                                   -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
 
-// L lanes per trajectory (1, 2 or 4).  At the optimizer's batch sizes (1e4 candidates = 313 warps on 592 schedulers) the
-// kernel is bound by the latency of ONE warp's instruction stream, a third of which is the 5 x NPH sin/cos pairs of a
-// step.  With L > 1 the lanes of a trajectory split those evaluations (all five stage times are known when the step
-// starts) and exchange the results by shuffle; everything else is computed redundantly, in lock step, by every lane of
-// the group, so the results are the L = 1 results bit for bit.  The host uses L > 1 for small batches only (see the launch).
-template <int D, int KA, int L, bool TRI>
-__global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dopri5Args a) {
+// One thread per trajectory.  (Two or four lanes per trajectory sharing the sin/cos work were tried for the optimizer's
+// batch sizes, where only half of the schedulers have a warp: bit-identical results, but the redundant remainder of the
+// step cost more than the split saved -- 3.97 / 4.68 ms against 2.95 ms at B = 1e4.)
+template <int D, int KA, bool TRI>
+__global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
   constexpr int NPH = DpShape<D, KA, TRI>::NPH;
-  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  if (b >= a.B) return;  // whole groups leave together
-  const int gl = threadIdx.x & (L - 1);
-  const int gbase = (threadIdx.x & 31) & ~(L - 1);
-  const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << gbase;
-  (void)gmask;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
   double yr[D], yi[D];
   {
     const double* src = a.y0 + (a.y0_batched ? b * 2 * D : 0);
@@ -243,7 +237,6 @@ __global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dop
   auto emit = [&](const double* vr, const double* vi) {
     double* o = outp + (long long)out_slot * 2 * D;
     out_slot++;
-    if (gl != 0) return;
 #pragma unroll
     for (int i = 0; i < D; i++) {
       double sr = 0, si = 0;
@@ -318,69 +311,27 @@ __global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dop
       break;
     }
     // ---- one attempted step.  The t-only part of the six new stages (five distinct times: stages 5 and 6 are both
-    // at t + dt) does not depend on the state.
-    if constexpr (L == 1) {
-      // computed first in a ROLLED loop: one copy of the index / table / sincos code instead of six keeps the step
-      // inside the instruction cache (the fully unrolled step spent 25 % of its cycles on instruction fetch with one
-      // warp per scheduler), and the five sets wait in local memory.
-      // The envelope look-up of stage s + 1 is issued before the sin/cos work of stage s, which hides its latency (it
-      // was 14 % of all stall samples when each iteration started with its own look-up).
-      DpCoef<D> cfs[5];
-      double2 env_next[KA];
-      dp_env<KA>(a, b, fma(dt, DP_ALPHA[0], t), env_next);
-#pragma unroll 1
-      for (int s = 0; s < 5; s++) {
-        double2 env[KA];
+    // at t + dt) does not depend on the state: the five envelope look-ups are issued first (their latency hides behind
+    // the sin/cos work), then all 5 x NPH sin/cos pairs as one block of independent chains; the per-stage coefficient
+    // sets are assembled between the stages, off the critical path.  (A rolled loop over the five times kept the code
+    // small but serialised them: 3.9 ms against 2.95 ms at cfg 5.)
+    {
+      constexpr int NU = 5 * NPH;
+      double2 envs[5][KA];
 #pragma unroll
-        for (int k = 0; k < KA; k++) env[k] = env_next[k];
-        if (s < 4) dp_env<KA>(a, b, fma(dt, DP_ALPHA[s + 1], t), env_next);
-        dp_coef<D, KA, TRI>(a, env, fma(dt, DP_ALPHA[s], t), cfs[s]);
-      }
-#pragma unroll
-      for (int s = 1; s < 7; s++) {
-        double tr[D], ti[D];
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          double ar = 0, ai = 0;
-#pragma unroll
-          for (int q = 0; q < s; q++) {
-            ar += DP_BETA[s - 1][q] * kr[q][i];
-            ai += DP_BETA[s - 1][q] * ki[q][i];
-          }
-          tr[i] = yr[i] + dt * ar;
-          ti[i] = yi[i] + dt * ai;
-        }
-        dp_apply<D, TRI>(a.emask, cfs[s < 6 ? s - 1 : 4], tr, ti, kr[s], ki[s]);
-      }
-    } else {
-      // the 5 x NPH sin/cos pairs of the step, dealt round-robin over the L lanes of the trajectory
-      constexpr int NU = 5 * NPH, UPL = (NU + L - 1) / L;
-      double usn[UPL], ucs[UPL];
+      for (int s = 0; s < 5; s++) dp_env<KA>(a, b, fma(dt, DP_ALPHA[s], t), envs[s]);
+      double usn[NU], ucs[NU];
       {
-        double ux[UPL];
+        double ux[NU];
 #pragma unroll
-        for (int q = 0; q < UPL; q++) {
-          int u = q * L + gl;
-          u = u < NU ? u : NU - 1;
-          const int s = u / NPH, n = u - s * NPH;
-          ux[q] = a.phase_freq[n] * fma(dt, DP_ALPHA[s], t);
-        }
-        dp_sincos_n<UPL>(dp_fast_range(a, t) && dp_fast_range(a, t + dt), ux, usn, ucs);
+        for (int u = 0; u < NU; u++) ux[u] = a.phase_freq[u % NPH] * fma(dt, DP_ALPHA[u / NPH], t);
+        dp_sincos_n<NU>(dp_fast_range(a, t) && dp_fast_range(a, t + dt), ux, usn, ucs);
       }
       DpCoef<D> cf;
 #pragma unroll
       for (int s = 1; s < 7; s++) {
         if (s < 6) {
-          double sn[NPH], cs[NPH];
-#pragma unroll
-          for (int n = 0; n < NPH; n++) {
-            const int u = (s - 1) * NPH + n;
-            sn[n] = __shfl_sync(gmask, usn[u / L], gbase + (u % L));
-            cs[n] = __shfl_sync(gmask, ucs[u / L], gbase + (u % L));
-          }
-          double2 env[KA];
-          dp_env<KA>(a, b, fma(dt, DP_ALPHA[s - 1], t), env);
-          dp_build<D, KA, TRI>(a, env, sn, cs, cf);
+          dp_build<D, KA, TRI>(a, envs[s - 1], usn + (s - 1) * NPH, ucs + (s - 1) * NPH, cf);
         }
         double tr[D], ti[D];
 #pragma unroll
@@ -414,8 +365,7 @@ __global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dop
       y1i[i] = dt * si + yi[i];
       er *= dt;
       ei *= dt;
-      const double tol = a.atol + a.rtol * sqrt(fmax(yr[i] * yr[i] + yi[i] * yi[i], y1r[i] * y1r[i] + y1i[i] * y1i[i]));
-      ratio += (er * er + ei * ei) / (tol * tol);
+      ratio += dp_err_term(er * er + ei * ei, fmax(yr[i] * yr[i] + yi[i] * yi[i], y1r[i] * y1r[i] + y1i[i] * y1i[i]), a.atol, a.rtol);
     }
     ratio *= 1.0 / D;  // MEAN SQUARE error ratio from here on: accept iff <= 1 (dp_step_factor)
     double new_dt = dt * dp_step_factor(ratio);
@@ -481,7 +431,6 @@ __global__ void __launch_bounds__(64, L == 4 ? 5 : 1) sv_dopri5_kernel(const Dop
     for (; next < a.T; next++)
       if (a.keep[next]) emit(nanv, nanv);
   }
-  if (gl != 0) return;
   if (a.nsteps) {
     a.nsteps[2 * b] = n_att;
     a.nsteps[2 * b + 1] = n_acc;
@@ -629,12 +578,6 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
       a.phase_freq[n++] = (a.emask & (1u << e2)) ? a.bohr[e2] : 0.0;
     }
   }
-  int lanes_forced = 0;
-  if (const char* ev = getenv("CASQ_DOPRI5_LANES")) lanes_forced = atoi(ev);
-  if (lanes_forced != 0 && lanes_forced != 1 && lanes_forced != 2 && lanes_forced != 4)
-    CASQ_FAIL(CASQ_ERR_INVALID, "CASQ_DOPRI5_LANES must be 1, 2 or 4");
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   // the batch is walked in windows that bound the envelope table (one window up to 2.6e5 points at cfg 5's 257 samples)
   const long long Bw = casq_env_table_window(KA, n_total, B);
   if ((rc = m->work2.ensure((size_t)KA * std::max(n_total, 1) * (size_t)Bw * sizeof(double2)))) return rc;
@@ -649,25 +592,15 @@ extern "C" int casq_solve_sv_dopri5(casq_model* m, int n_slots, const casq_pulse
     a.nsteps = nsteps_dev ? (long long*)nsteps_dev + 2 * b0 : nullptr;
     a.status = status_dev ? status_dev + b0 : nullptr;
     bool launched = false;
-    // lanes per trajectory: more than one only while every warp still has a scheduler to itself (4 per SM); beyond that
-    // the redundant work of the extra lanes costs more than the shorter instruction stream saves (B = 1e4 on B200:
-    // 4.8 / 5.3 / 6.0 ms with 1 / 2 / 4 lanes; B = 3e3: 4.8 / 4.6 / 4.3 ms)
-#define LAUNCH_L(D_, K_, L_, T_)                                                                                         \
-  if (!launched && (lanes_forced == 0 || lanes_forced == L_)) {                                                         \
-    const long long grid = (Bc * L_ + block - 1) / block;                                                               \
-    if (L_ == 1 || lanes_forced == L_ || grid * (block / 32) <= 4LL * n_sm) {                                           \
-      sv_dopri5_kernel<D_, K_, L_, T_><<<(unsigned)grid, block, 0, st>>>(a);                                            \
-      launched = true;                                                                                                  \
-    }                                                                                                                   \
-  }
-#define LAUNCH(D_, K_, T_)                                                                                               \
-  if (d == D_ && KA == K_ && tri == T_) {                                                                               \
-    LAUNCH_L(D_, K_, 4, T_) LAUNCH_L(D_, K_, 2, T_) LAUNCH_L(D_, K_, 1, T_)                                             \
+    const unsigned grid = (unsigned)((Bc + block - 1) / block);
+#define LAUNCH(D_, K_, T_)                                      \
+  if (d == D_ && KA == K_ && tri == T_) {                      \
+    sv_dopri5_kernel<D_, K_, T_><<<grid, block, 0, st>>>(a);   \
+    launched = true;                                           \
   }
     LAUNCH(2, 1, true) LAUNCH(2, 2, true) LAUNCH(3, 1, true) LAUNCH(3, 2, true) LAUNCH(4, 1, true) LAUNCH(4, 2, true)
     LAUNCH(3, 1, false) LAUNCH(3, 2, false) LAUNCH(4, 1, false) LAUNCH(4, 2, false)
 #undef LAUNCH
-#undef LAUNCH_L
     if (!launched) CASQ_FAIL(CASQ_ERR_UNSUPPORTED, "casq_solve_sv_dopri5: no kernel variant for dim %d, %d channels", d, KA);
   }
   CASQ_CUDA(cudaGetLastError());

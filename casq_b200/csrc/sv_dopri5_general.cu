@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(32 * DG_WARPS) sv_dopri5_general_kernel(const 
       y1i[r] = dt * si + yi[r];
       er *= dt;
       ei *= dt;
-      const double tol = a.atol + a.rtol * fmax(hypot(yr[r], yi[r]), hypot(y1r[r], y1i[r]));
-      if (own[r]) ratio += (er * er + ei * ei) / (tol * tol);
+      if (own[r])
+        ratio += dp_err_term(er * er + ei * ei, fmax(yr[r] * yr[r] + yi[r] * yi[r], y1r[r] * y1r[r] + y1i[r] * y1i[r]), a.atol, a.rtol);
     }
     ratio = dg_warp_sum(ratio) / d;  // MEAN SQUARE error ratio from here on: accept iff <= 1 (dp_step_factor)
     double new_dt = dt * dp_step_factor(ratio);
