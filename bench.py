@@ -442,8 +442,6 @@ def run_ours(args) -> None:
 
     # Sharded runs write their results straight into rank 0's memory (peer stores over NVLink from the kernel's epilogue)
     peer = PeerResultBuffer((B, 2, 3), torch.complex128, dev, dst=0) if world > 1 else None
-    if peer is not None:
-        out = peer.slot
 
     def barrier():
         if world > 1:
@@ -458,11 +456,15 @@ def run_ours(args) -> None:
         return float(t.item())
 
     def hot_step():
-        """table kernel + RK4 kernel (+ the one result gather when sharded)."""
+        """table kernel + RK4 kernel (+ the hand-over of the final states to rank 0 when sharded)."""
         model.invalidate_cache()
-        engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
-        if world > 1 and not os.environ.get("CASQ_BENCH_NO_GATHER"):  # the one exchange of the path: final states on rank 0
-            peer.sync()                                                # (the env knob is a diagnosis aid: pace of the slowest GPU)
+        if peer is None:
+            engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
+            return
+        engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=peer.slot)  # stores land in rank 0's HBM
+        if not os.environ.get("CASQ_BENCH_NO_GATHER"):  # (the env knob is a diagnosis aid: pace of the slowest GPU)
+            peer.sync()     # producers: raise a flag and go on; rank 0: wait for all 1e5 x N final states
+            peer.release()  # rank 0 is done with them (nothing consumes them in the bench)
 
     def timed(fn, k, warm=0):
         for _ in range(warm):
@@ -492,6 +494,17 @@ def run_ours(args) -> None:
             engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
 
         ms_kernel = timed(kernel_only, args.steps)
+    peer_ok = None
+    if peer is not None:
+        # the hand-over checked once against a plain NCCL gather of locally stored results (bit-equal on rank 0)
+        engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=out)
+        want = gather_batch(out, B * world, dst=0)
+        engine.solve_sv_rk4(model, slots, dev_params, y0, t_span, max_dt, out=peer.slot)
+        peer.sync()
+        if rank == 0:
+            peer_ok = bool(torch.equal(peer.result(), want))
+        peer.release()
+        peer.drain()
     ms_step = max_over_ranks(ms_step)
     ms_kernel = max_over_ranks(ms_kernel)
 
@@ -525,15 +538,17 @@ def run_ours(args) -> None:
         sp = sweep_params(0)
         sub_params = engine.pack_params([dict(amp=sp["amp"][lo:hi], angle=0.0, sigma=SIGMA, beta=sp["beta"][lo:hi])], device=dev)
         peer_s = PeerResultBuffer((-(-B // world), 2, 3), torch.complex128, dev, dst=0)
-        sub_out = peer_s.slot[: hi - lo]
 
         def strong_step():
             model.invalidate_cache()
-            engine.solve_sv_rk4(model, slots, sub_params, y0, t_span, max_dt, out=sub_out)
+            engine.solve_sv_rk4(model, slots, sub_params, y0, t_span, max_dt, out=peer_s.slot[: hi - lo])
             peer_s.sync()
+            peer_s.release()
 
         barrier()
-        ms_strong = max_over_ranks(timed(strong_step, args.steps, warm=args.warmup))
+        ms_strong = timed(strong_step, args.steps, warm=args.warmup)
+        peer_s.drain()
+        ms_strong = max_over_ranks(ms_strong)
         barrier()
         strong = {"global_points": B, "points_per_gpu": B // world, "ms_per_step": ms_strong, "value": B / (ms_strong * 1e-3),
                   "unit": "trajectories/s", "scaling": "strong"}
@@ -589,6 +604,8 @@ def run_ours(args) -> None:
             "cpu_baseline": cpu,
             "max_state_err": max_state_err,
             "strong_scaling": strong,
+            "peer_handover": None if peer is None else {"fused_into_kernel_stores": peer.fused, "equals_nccl_gather": peer_ok,
+                                                        "ring_depth": peer.depth},
             "configs": configs,
             "clocks": clocks.summary(),
         }))

@@ -73,7 +73,10 @@ def _peer_worker(rank, world, port, q):
         assert not buf.fused and buf.slot.shape == (4, 2, 3)  # CPU / gloo: the collective fallback
         buf.slot.copy_(torch.full((4, 2, 3), complex(rank + 1, -rank), dtype=torch.complex128))
         buf.sync()
-        q.put((rank, buf.result()))
+        res = buf.result()
+        buf.release()  # no-ops in the fallback, part of the call order every rank follows
+        buf.drain()
+        q.put((rank, res))
     finally:
         dist.destroy_process_group()
 
