@@ -4,7 +4,7 @@
 #include "common.cuh"
 
 // numpy float floor-division a // b (b > 0), then clip to [-1, n_total]
-__device__ __forceinline__ int dev_sample_index(double t, double dt, int n_total) {
+static __device__ __noinline__ int dev_sample_index(double t, double dt, int n_total) {
   double mod = fmod(t, dt);
   double div = (t - mod) / dt;
   if (mod != 0.0 && (mod < 0)) div -= 1.0;
@@ -18,16 +18,20 @@ __device__ __forceinline__ int dev_sample_index(double t, double dt, int n_total
   return (int)fl;
 }
 
-// The same index without the iterative fmod: a guess from one multiplication, corrected by the EXACT sign of the
-// remainder t - q dt (one FMA).  Only a remainder that rounds to exactly dt is ambiguous; that case (times that are
-// exact multiples of dt) takes the reference path above.
+// The same index without the iterative fmod and without the conversion unit: q = NEAREST integer to t / dt through the
+// 2^52 + 2^51 constant (the integer is the low word of the sum), then the EXACT sign of the remainder t - q dt (one FMA:
+// the rounded result has the sign of the exact one) says whether floor(t / dt) is q or q - 1.  With the nearest integer
+// the remainder lies in [-dt/2, dt/2], so the ambiguous "remainder rounds to dt" case of a floor-based guess cannot
+// occur.  Quotients beyond the int range take the reference path above.
 __device__ __forceinline__ int dev_sample_index_fast(double t, double dt, double inv_dt, int n_total) {
-  double q = floor(t * inv_dt);
+  const double x = t * inv_dt;
+  if (!(fabs(x) < 2.0e9)) return dev_sample_index(t, dt, n_total);
+  const double magic = 6755399441055744.0;
+  const double m = x + magic;
+  const double q = m - magic;
   const double r = fma(-q, dt, t);
-  if (r == dt) return dev_sample_index(t, dt, n_total);
-  q += (r < 0.0) ? -1.0 : (r > dt ? 1.0 : 0.0);
-  // the conversion saturates, so the clip can be done on the integer (two IMNMX instead of two emulated fp64 min/max)
-  return min(max(__double2int_rz(q), -1), n_total);
+  const int qi = __double2loint(m) - (r < 0.0 ? 1 : 0);
+  return min(max(qi, -1), n_total);
 }
 
 // Branch-free fp64 sincos for |x| < 1e5 (phases reach ~2e3 rad here): two-FMA Cody-Waite reduction by pi/2 and the

@@ -81,6 +81,13 @@ struct DpShape {
   static constexpr int NPH = KA + EP;         // phases per stage time
 };
 
+// the library routine (any argument), kept out of line: 15 inlined copies of its slow path made the step's code 3x larger
+static __device__ __noinline__ double2 dp_sincos_slow(double x) {
+  double s, c;
+  sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+
 // sin / cos of N phases; `fast`: every argument is inside the range of the branch-free routine (the caller tests
 // |t| max|freq| once instead of reducing over the arguments)
 template <int N>
@@ -90,7 +97,11 @@ __device__ __forceinline__ void dp_sincos_n(bool fast, const double* x, double* 
     for (int n = 0; n < N; n++) dp_sincos_fast(x[n], &sn[n], &cs[n]);
   } else {
 #pragma unroll
-    for (int n = 0; n < N; n++) sincos(x[n], &sn[n], &cs[n]);
+    for (int n = 0; n < N; n++) {
+      const double2 r = dp_sincos_slow(x[n]);
+      sn[n] = r.x;
+      cs[n] = r.y;
+    }
   }
 }
 __device__ __forceinline__ bool dp_fast_range(const Dopri5Args& a, double t) { return fabs(t) * a.freq_max < DP_TRIG_MAX; }
@@ -295,11 +306,12 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
   int status = 0;
   int next = 1;  // next merged time point to produce
   long long i_target = 0;
+  double target = a.tpts[1 < a.T ? 1 : 0];  // a.tpts[next], reloaded only when `next` moves (not a load per attempt)
   while (next < a.T) {
-    const double target = a.tpts[next];
     if (!(t < target)) {
       // cannot happen before the first step (t0 < t1); guard against equal points
       next++;
+      if (next < a.T) target = a.tpts[next];
       continue;
     }
     if (i_target >= a.mxstep) {
@@ -411,6 +423,7 @@ __global__ void __launch_bounds__(64) sv_dopri5_kernel(const Dopri5Args a) {
           next++;
           i_target = 0;
         }
+        if (next < a.T) target = a.tpts[next];
       }
       t = t_new;
 #pragma unroll
