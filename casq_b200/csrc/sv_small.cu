@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(128) __maxnreg__((SmallOcc<D, KA, RWA, HAS_S>:
   }
 }
 
-// Out-of-line envelope refresh for two trajectories (boundary steps of sv_rk4_small2_kernel).
+// Out-of-line envelope refresh for two trajectories (boundary steps of sv_rk4_small2_kernel).  (A per-solve table of all
+// samples, as the Dopri5 and propagator kernels use, was measured here too: the table kernel costs what the in-line
+// evaluation on one step in 40 costs -- 9.73-9.91 ms with it, 9.83 without -- so it is not used.)
 __device__ __noinline__ void small_env_refresh2(const SmallArgs* __restrict__ ap, long long b0, long long b1, int gidx, dcplx* out) {
   casq_channel_envelopes<1>(ap->slots, ap->params, ap->B, b0, gidx, out);
   casq_channel_envelopes<1>(ap->slots, ap->params, ap->B, b1, gidx, out + 1);
@@ -607,6 +609,10 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
       __syncthreads();
       const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
       const unsigned fast = __ldg(a.fast_mask + mask_pos + c);
+      // The entry of stage 4 of a step (time t + h) is the entry of stage 1 of the next one: it stays in registers, so a
+      // step starts its first matvec without waiting for shared memory (that wait was 8 % of the busy warps' stall samples).
+      Ent E;
+      E.load(tab);
       for (int s = 0; s < ns; s++) {
         // envelope values seen by stage 1 / stages 2,3 / stage 4: all equal to the cached one except on the ~1 step in
         // 40 that touches a sample boundary, where an out-of-line refresh supplies the new sample
@@ -642,9 +648,7 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
         }
         {
           const double* ent = tab + 2 * s * Ent::W;
-          Ent E;
           double k0r[D], k0i[D], k1r[D], k1i[D], a0r[D], a0i[D], a1r[D], a1i[D], t0r[D], t0i[D], t1r[D], t1i[D];
-          E.load(ent);
           double z0 = eA0.re * E.c[0] - eA0.im * E.s[0], z1 = eA1.re * E.c[0] - eA1.im * E.s[0];
           matvec2(E, y0r, y0i, y1r, y1i, k0r, k0i, k1r, k1i);
           double c0 = h2 * z0, g0 = h6 * z0, c1 = h2 * z1, g1 = h6 * z1;
