@@ -240,6 +240,22 @@ def test_dopri5_smooth_case_is_step_exact():
         assert np.abs(got.cpu().numpy() - want).max() < 1e-12
 
 
+def test_dopri5_far_from_the_schedule_takes_the_reference_paths():
+    """t / dt beyond the int range and phases beyond the branch-free sincos: the out-of-line reference routines (numpy
+    floor-division index, library sincos) take over.  Nothing is played there and the frame is H0, so the state must not
+    move, the error estimate is exactly zero and the controller grows the step tenfold per attempt like the oracle's."""
+    om, nm, ch = _models((0,), "full")
+    p = dict(amp=np.array([0.4, 0.7]), angle=0.0, sigma=8.0, beta=np.array([1.0, -2.0]))
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", 32)], [p])
+    y0 = np.array([0.6, 0.0, 0.8j])
+    span = (1.0, 1.0 + 32 * DT)  # t / dt = 4.5e9
+    _, want, steps = O.dopri5_jax_solve(om, samples, y0, span, rtol=1e-8, atol=1e-8)
+    got, ns, status = engine.solve_sv_dopri5(nm, [("drag", 0, 0, 32)], engine.pack_params([p], device="cuda"), y0, span,
+                                             rtol=1e-8, atol=1e-8, return_stats=True)
+    assert int(status.abs().sum()) == 0 and np.array_equal(ns.cpu().numpy(), steps)
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-14 and np.abs(got[:, -1].cpu().numpy() - y0).max() < 1e-14
+
+
 def test_dopri5_mxstep_reports_failure():
     om, nm, ch = _models((0,), "full")
     p = dict(amp=0.5, angle=0.0, sigma=8.0, beta=1.0)
