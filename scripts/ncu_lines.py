@@ -34,20 +34,32 @@ for l in lines[start + 1:]:
         continue
     if re.match(r"\s*/\*[0-9a-f]+\*/\s+.*?;", l):
         seq.append(cur)
-hdr, data = rows[1], rows[2:]
-i_s, i_e = hdr.index("# Samples"), hdr.index("Instructions Executed")
-agg, total = collections.defaultdict(lambda: [0, 0, 0]), 0
-for k, r in enumerate(data):
+# the report lists every captured launch in turn: "Kernel Name" row, column header row, one row per instruction
+demangled = None
+agg, total, launches, k = collections.defaultdict(lambda: [0, 0, 0]), 0, 0, 0
+hdr = i_s = i_e = None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        demangled, k = r[1], -1
+        continue
+    if r and r[0] == "Address":
+        hdr, k = r, 0
+        i_s, i_e = hdr.index("# Samples"), hdr.index("Instructions Executed")
+        launches += 1
+        continue
+    if hdr is None or k < 0:
+        continue
     try:
         s, e = int(r[i_s]), int(r[i_e])
     except (ValueError, IndexError):
         continue
     key = seq[k] if k < len(seq) and seq[k] else ("?", 0)
+    k += 1
     agg[key][0] += s
     agg[key][1] += 1
     agg[key][2] += e
     total += s
-print(f"{len(seq)} instructions in the cubin, {len(data)} in the report, {total} stall samples")
+print(f"{len(seq)} instructions in the cubin, {launches} launch(es) in the report (all must be {fun}), {total} stall samples")
 cache = {}
 for key, (s, n, e) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     path = os.path.join(src_dir, key[0])
