@@ -252,3 +252,21 @@ def test_lindblad_rhs_restructured_form_equals_textbook_form():
         LdL = Lt.conj().T @ Lt
         want = want + Lt @ rho @ Lt.conj().T - 0.5 * (LdL @ rho + rho @ LdL)
     assert np.abs(got - want).max() < 1e-9 * np.abs(want).max()
+
+
+def test_dopri5_tableau_is_anchored_to_scipy_rk45():
+    """The Dormand-Prince constants the oracle (and, through the GPU parity tests, the CUDA steppers) use, checked against an
+    INDEPENDENT implementation that ships in this image: scipy.integrate.RK45.  Nodes, stage matrix and 5th-order weights are
+    the same numbers; the dense-output mid-point weights equal scipy's interpolation polynomial at theta = 1/2; the error
+    weights are jax.experimental.ode's variant, which is exactly -2/3 of scipy's E (same embedded pair, scaled estimate)."""
+    from scipy.integrate import RK45
+
+    from oracle import solvers as S
+
+    assert np.array_equal(S._DP_ALPHA[:5], RK45.C[1:6])
+    assert np.abs(S._DP_BETA[:5, :5] - RK45.A[1:6, :5]).max() == 0.0
+    assert np.abs(S._DP_BETA[5, :6] - RK45.B).max() == 0.0  # FSAL: the last stage row is the 5th-order solution
+    assert np.abs(S._DP_CSOL[:6] - RK45.B).max() == 0.0 and S._DP_CSOL[6] == 0.0
+    half = RK45.P @ np.array([0.5, 0.25, 0.125, 0.0625])
+    assert np.abs(S._DP_CMID - half).max() < 5e-16  # scipy evaluates a cubic in theta: rounding of the sum
+    assert np.abs(S._DP_CERR - (-2.0 / 3.0) * RK45.E).max() < 1e-16
