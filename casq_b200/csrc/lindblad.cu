@@ -438,6 +438,40 @@ static int lindblad_run_chain(casq_model* m, const ChainPlan& cp, Builder& bld, 
     }
     CASQ_CUDA(cudaGetLastError());
   }
+  if (getenv("CASQ_LB_CHECK_PLAN")) {
+    // Self-check of the gather plan (compute-sanitizer is not available everywhere): every nine-row piece a block fetches,
+    // from its own tiles or through a list offset, must lie inside one matrix plus the zero-filled slack around the
+    // work buffers.  A piece past the end of a trajectory's matrix would read its neighbour's rows (harmless only while the
+    // coefficient is zero), a piece outside the slack is an out-of-bounds access.
+    std::vector<LcList> plan((size_t)npairs * LC_WARPS * 3);
+    std::vector<int> pij(2 * (size_t)npairs);
+    CASQ_CUDA(cudaStreamSynchronize(st));
+    CASQ_CUDA(cudaMemcpy(plan.data(), dev + o_plan, plan.size() * sizeof(LcList), cudaMemcpyDeviceToHost));
+    CASQ_CUDA(cudaMemcpy(pij.data(), dev + o_pij, pij.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const long long TSZ = (long long)LC_T * LC_TS, piece = 9LL * LC_TS;
+    long long lo = 0, hi = 0, worst_in = 0;
+    for (int pr = 0; pr < npairs; pr++)
+      for (int gq = 0; gq < LC_WARPS; gq++) {
+        const long long I = pij[2 * pr], J = pij[2 * pr + 1];
+        const long long tI = (I * ntile + J) * TSZ + 9LL * gq * LC_TS, tJ = (J * ntile + I) * TSZ + 9LL * gq * LC_TS;
+        for (int seg = 0; seg < 3; seg++) {
+          const LcList& L = plan[((size_t)pr * LC_WARPS + gq) * 3 + seg];
+          if (L.n < 0 || L.n > 15) CASQ_FAIL(CASQ_ERR_INVALID, "chain plan: list (%d,%d,%d) has %d terms", pr, gq, seg, L.n);
+          for (int i = 0; i < L.n; i++) {
+            const long long start = (seg == 0 ? tJ : tI) + L.off[i], end = start + piece;
+            lo = std::min(lo, start);
+            hi = std::max(hi, end - (long long)n_pad);
+            if (start >= 0 && end <= (long long)n_pad) worst_in++;
+          }
+        }
+      }
+    if (-lo > (long long)slack || hi > (long long)slack)
+      CASQ_FAIL(CASQ_ERR_INVALID, "chain plan: a gather piece leaves the buffers (%lld elements before, %lld behind a matrix; slack %zu)", -lo,
+                hi, slack);
+    if (getenv("CASQ_LB_CHECK_PLAN_VERBOSE"))
+      fprintf(stderr, "chain plan: %lld pieces inside their matrix, furthest %lld elements before / %lld behind (slack %zu)\n", worst_in, -lo, hi,
+              slack);
+  }
   int tma_stages = LC_DEFAULT_TMA_STAGES;
   if (const char* e = getenv("CASQ_LB_TMA_STAGES")) tma_stages = atoi(e) & 15;
   if (getenv("CASQ_LB_NO_TMA")) tma_stages = 0;

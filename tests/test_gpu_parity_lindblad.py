@@ -220,6 +220,7 @@ def test_lindblad_d243_cfg4_operators_vs_oracle(scale, rho0_kind, monkeypatch):
     else:
         rho0 = _random_density_matrices(rng, B, 243)
         want = np.concatenate([O.lindblad_rk4_solve(om, samples[b:b + 1], rho0[b], span, DT / 4)[1] for b in range(B)])
+    monkeypatch.setenv("CASQ_LB_CHECK_PLAN", "1")  # the library verifies that every gather piece stays inside the work buffers
     for parts in ("1", "2"):
         monkeypatch.setenv("CASQ_LB_PARTS", parts)
         rho, pops = engine.solve_lindblad_rk4(nm, [("drag", ch.index("d0"), 0, dur)], engine.pack_params([p], device="cuda"),
