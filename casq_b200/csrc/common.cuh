@@ -77,6 +77,10 @@ struct casq_model {
   long long tab_NT = 0;   // shape of the cached fixed-step grid (small RK4 path)
   int tab_n_pieces = 0, tab_piece0_steps = 0;
   DeviceBuf slice_buf;    // ticket queue and hand-over state of the time-sliced headline kernel
+  // constant-table variant of the headline kernel (sv_small.cu, ConstTab): offset table + frame phasors (host, cached with
+  // the grid) and the per-chunk phasor table (device)
+  std::vector<double> small_ct;
+  DeviceBuf ct_chunk;
   // pinned host staging of the small RK4 path's grid upload (pageable cudaMemcpyAsync synchronises the stream per copy)
   void* stage_h = nullptr;
   size_t stage_bytes = 0;

@@ -265,7 +265,7 @@ extern "C" int casq_model_create(casq_model** out, int dim, int n_channels, cons
 extern "C" void casq_model_destroy(casq_model* m) {
   if (!m) return;
   DeviceBuf* bufs[] = {&m->tab, &m->tab_idx, &m->tab_times, &m->pieces_n, &m->pieces_h, &m->consts,
-                       &m->work0, &m->work1, &m->work2, &m->work3, &m->slice_buf};
+                       &m->work0, &m->work1, &m->work2, &m->work3, &m->slice_buf, &m->ct_chunk};
   for (DeviceBuf* b : bufs) b->release();
   if (m->stage_h) cudaFreeHost(m->stage_h);
   if (m->stage_ev) cudaEventDestroy(m->stage_ev);

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "common.cuh"
 #include "envelope.cuh"
@@ -463,6 +464,29 @@ __device__ __noinline__ void small_env_refresh2(const SmallArgs* __restrict__ ap
 // state (17 doubles per thread) is handed over through global memory at segment boundaries and the task of the next
 // segment goes to the worker that has waited longest, so the idle slots rotate over the SMs and every scheduler carries
 // the same average load.  Same arithmetic in the same order: results are bit-identical to the unsliced kernel.
+// CT (constant-table) variant of the two-trajectory kernel, one piece on a uniform grid.  The fp64 pipe issues a DFMA per
+// 2.2 cycles only while at most two of its three operands come out of the vector register file (3.0 cycles with three;
+// profiles/r02_fp64_operand_microbench.txt), and the one operand that can come from elsewhere is a UNIFORM register, which
+// ptxas fills from the constant bank (kernel parameters) and from nothing else.  The stage table (987 kB for the headline
+// sweep) cannot live there -- but its phases factorise: t = t0_c + m h/2 inside chunk c, so
+//   T_e e^{i(e_i-e_j) t} = e^{i e_i t0_c} [T_e e^{i(e_i-e_j) m h/2}] e^{-i e_j t0_c},   e^{i w t} = e^{i w t0_c} e^{i w m h/2}.
+// The bracket depends on the offset m only: 65 entries, 3 kB, passed as a kernel PARAMETER.  The chunk phases are absorbed
+// into the state: the kernel integrates u_j = e^{-i e_j t0_c} y_j, a constant diagonal change of variables inside a chunk
+// (RK4 on a linear equation commutes with it exactly; only rounding differs), re-phased at every chunk boundary by
+// e^{-i e_j (t0_{c+1} - t0_c)} from a small per-chunk table, and the carrier phase e^{i w t0_c} is folded into the cached
+// envelope value.  No shared-memory staging, no block barrier in the time loop.
+template <int NE>
+struct ConstTab {
+  double2 car[2 * SMALL_CHUNK_STEPS + 1];      // (cos, sin)(2 pi nu m h/2)
+  double2 T[2 * SMALL_CHUNK_STEPS + 1][NE];    // T_e e^{i (e_i - e_j) m h/2}
+  double2 f_start[SMALL_MAXD];                 // e^{-i e_j t0_0}: rotating frame -> frame of chunk 0
+  double2 f_end[SMALL_MAXD];                   // e^{+i e_j t0_last}: frame of the last chunk -> rotating frame
+  const double2* chunk;                        // [n_chunks][2 + SMALL_MAXD]: e^{i w t0_c}, e^{i w (t0_{c+1}-t0_c)}, e^{-i e_j (t0_{c+1}-t0_c)}
+};
+struct NoConstTab {
+  int unused;
+};
+
 struct SliceCtl {
   unsigned* head;      // next ticket to hand out
   unsigned* tail;      // next queue slot to fill
@@ -473,9 +497,24 @@ struct SliceCtl {
   int n_jobs, nseg, chunks_per_seg;
 };
 
-template <int D, bool TRI, bool SLICED>
-__global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, const SliceCtl ctl) {
+#ifndef SMALL2_MINBLOCKS
+#define SMALL2_MINBLOCKS 1
+#endif
+template <int D, bool TRI, bool SLICED, bool CT>
+__global__ void __launch_bounds__(64, SMALL2_MINBLOCKS) sv_rk4_small2_kernel(const SmallArgs a, const SliceCtl ctl,
+                                                           const typename std::conditional<CT, ConstTab<Couplings<D, TRI>::NE>, NoConstTab>::type ct) {
   typedef Entry<D, 1, false, false, TRI> Ent;
+  constexpr int NE = Couplings<D, TRI>::NE;
+  // y <- phase * y, component-wise (frame changes of the CT variant)
+  auto rephase = [&](double* yr, double* yi, const double2* ph) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const double2 f = ph[i];
+      const double r = yr[i] * f.x - yi[i] * f.y, im = yr[i] * f.y + yi[i] * f.x;
+      yr[i] = r;
+      yi[i] = im;
+    }
+  };
   const long long half = (a.B + 1) / 2;
   __shared__ int s_task;
  for (;;) {  // SLICED: one iteration per task
@@ -552,6 +591,10 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
     init(b0, y0r, y0i);
     init(b1, y1r, y1i);
     if (a.keep[0]) emit();
+    if constexpr (CT) {
+      rephase(y0r, y0i, ct.f_start);
+      rephase(y1r, y1i, ct.f_start);
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -571,7 +614,20 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
   constexpr int kChunk = SMALL_CHUNK_STEPS, kEnt = 2 * kChunk + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* const sm_tab0 = reinterpret_cast<double*>(smem_raw);
+  // CT: table entry of offset m from the constant bank (uniform-register operands)
+  auto load_ct = [&](Ent& E, int m) {
+    if constexpr (CT) {
+      E.c[0] = ct.car[m].x;
+      E.s[0] = ct.car[m].y;
+#pragma unroll
+      for (int e = 0; e < NE; e++) {
+        E.Tr[0][e] = ct.T[m][e].x;
+        E.Ti[0][e] = ct.T[m][e].y;
+      }
+    }
+  };
   auto stage = [&](int buf, long long first, int n_ent) {
+    if (CT) return;
     const char* src = reinterpret_cast<const char*>(a.table + first * Ent::W);
     const unsigned dst = (unsigned)__cvta_generic_to_shared(sm_tab0 + buf * (kEnt * Ent::W));
     const int bytes = n_ent * Ent::W * 8;
@@ -599,20 +655,36 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
     for (int c = c_lo; c < c_hi; c++) {
       const int s0 = c * kChunk;
       const int ns = (n - s0) < kChunk ? (n - s0) : kChunk;
-      if (c + 1 < c_hi) {
-        const int s1 = s0 + kChunk;
-        stage((c + 1) & 1, pos + 2 * s1, 2 * ((n - s1) < kChunk ? (n - s1) : kChunk) + 1);
-        asm volatile("cp.async.wait_group 1;");
-      } else {
-        asm volatile("cp.async.wait_group 0;");
+      if (!CT) {
+        if (c + 1 < c_hi) {
+          const int s1 = s0 + kChunk;
+          stage((c + 1) & 1, pos + 2 * s1, 2 * ((n - s1) < kChunk ? (n - s1) : kChunk) + 1);
+          asm volatile("cp.async.wait_group 1;");
+        } else {
+          asm volatile("cp.async.wait_group 0;");
+        }
+        __syncthreads();
       }
-      __syncthreads();
       const double* tab = sm_tab0 + (c & 1) * (kEnt * Ent::W);
       const unsigned fast = __ldg(a.fast_mask + mask_pos + c);
+      // CT: the cached envelope values carry the carrier phase of this chunk's base time
+      auto set_env = [&](const dcplx* fresh) {
+        if constexpr (CT) {
+          const double2 P = __ldg(ct.chunk + (long long)c * (2 + SMALL_MAXD));
+          env0.re = fresh[0].re * P.x - fresh[0].im * P.y;
+          env0.im = fresh[0].re * P.y + fresh[0].im * P.x;
+          env1.re = fresh[1].re * P.x - fresh[1].im * P.y;
+          env1.im = fresh[1].re * P.y + fresh[1].im * P.x;
+        } else {
+          env0 = fresh[0];
+          env1 = fresh[1];
+        }
+      };
       // The entry of stage 4 of a step (time t + h) is the entry of stage 1 of the next one: it stays in registers, so a
       // step starts its first matvec without waiting for shared memory (that wait was 8 % of the busy warps' stall samples).
       Ent E;
-      E.load(tab);
+      if (CT) load_ct(E, 0);
+      else E.load(tab);
       for (int s = 0; s < ns; s++) {
         // envelope values seen by stage 1 / stages 2,3 / stage 4: all equal to the cached one except on the ~1 step in
         // 40 that touches a sample boundary, where an out-of-line refresh supplies the new sample
@@ -624,24 +696,21 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
           if (ia != cur_idx) {
             cur_idx = ia;
             small_env_refresh2(a.self_dev, b0, b1, ia, fresh);
-            env0 = fresh[0];
-            env1 = fresh[1];
+            set_env(fresh);
           }
           eA0 = env0;
           eA1 = env1;
           if (ib != cur_idx) {
             cur_idx = ib;
             small_env_refresh2(a.self_dev, b0, b1, ib, fresh);
-            env0 = fresh[0];
-            env1 = fresh[1];
+            set_env(fresh);
           }
           eB0 = env0;
           eB1 = env1;
           if (ic != cur_idx) {
             cur_idx = ic;
             small_env_refresh2(a.self_dev, b0, b1, ic, fresh);
-            env0 = fresh[0];
-            env1 = fresh[1];
+            set_env(fresh);
           }
           eC0 = env0;
           eC1 = env1;
@@ -663,7 +732,8 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
             a1r[i] = fma(g1, k1r[i], y1r[i]);
             a1i[i] = fma(g1, k1i[i], y1i[i]);
           }
-          E.load(ent + Ent::W);
+          if (CT) load_ct(E, 2 * s + 1);
+          else E.load(ent + Ent::W);
           z0 = eB0.re * E.c[0] - eB0.im * E.s[0];
           z1 = eB1.re * E.c[0] - eB1.im * E.s[0];
           matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
@@ -696,7 +766,8 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
             a1r[i] = fma(g1, k1r[i], a1r[i]);
             a1i[i] = fma(g1, k1i[i], a1i[i]);
           }
-          E.load(ent + 2 * Ent::W);
+          if (CT) load_ct(E, 2 * s + 2);
+          else E.load(ent + 2 * Ent::W);
           z0 = eC0.re * E.c[0] - eC0.im * E.s[0];
           z1 = eC1.re * E.c[0] - eC1.im * E.s[0];
           matvec2(E, t0r, t0i, t1r, t1i, k0r, k0i, k1r, k1i);
@@ -711,11 +782,33 @@ __global__ void __launch_bounds__(64) sv_rk4_small2_kernel(const SmallArgs a, co
           }
         }
       }
-      __syncthreads();
+      if constexpr (CT) {
+        if (c + 1 < n_chunks) {  // into the frame of the next chunk (also what a hand-over stores)
+          const double2* cp = ct.chunk + (long long)c * (2 + SMALL_MAXD);
+          const double2 Q = __ldg(cp + 1);
+          double2 R[D];
+#pragma unroll
+          for (int i = 0; i < D; i++) R[i] = __ldg(cp + 2 + i);
+          rephase(y0r, y0i, R);
+          rephase(y1r, y1i, R);
+          const double e0r = env0.re * Q.x - env0.im * Q.y, e0i = env0.re * Q.y + env0.im * Q.x;
+          const double e1r = env1.re * Q.x - env1.im * Q.y, e1i = env1.re * Q.y + env1.im * Q.x;
+          env0.re = e0r;
+          env0.im = e0i;
+          env1.re = e1r;
+          env1.im = e1i;
+        }
+      } else {
+        __syncthreads();
+      }
     }
     pos += 2LL * n + 1;
     mask_pos += n_chunks;
     if (!SLICED || seg == ctl.nseg - 1) {
+      if constexpr (CT) {
+        rephase(y0r, y0i, ct.f_end);
+        rephase(y1r, y1i, ct.f_end);
+      }
       if (a.keep[p + 1]) emit();
     }
   }
@@ -986,6 +1079,54 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
       }
     sv_table_kernel<<<(unsigned)((NT + 127) / 128), 128, 0, st>>>(ta);
     CASQ_CUDA(cudaGetLastError());
+    // constant-table variant (ConstTab): offset table and frame phasors on the host, per-chunk phasors on the device
+    m->small_ct.clear();
+    if (n_pieces == 1 && KA == 1 && !m->rwa && !has_s) {
+      constexpr int kEnt = 2 * SMALL_CHUNK_STEPS + 1;
+      const int n0 = g.piece_nsteps[0];
+      const int n_chunks0 = (n0 + SMALL_CHUNK_STEPS - 1) / SMALL_CHUNK_STEPS;
+      const double hh = 0.5 * g.piece_h[0], w = ta.two_pi_nu[0];
+      std::vector<double>& v = m->small_ct;
+      v.assign((size_t)2 * kEnt + (size_t)2 * kEnt * NE + 4 * SMALL_MAXD, 0.0);
+      double* car = v.data();
+      double* Tt = car + 2 * kEnt;
+      double* fs = Tt + (size_t)2 * kEnt * NE;
+      double* fe_ = fs + 2 * SMALL_MAXD;
+      for (int mm = 0; mm < kEnt; mm++) {
+        const double dl = mm * hh;
+        car[2 * mm] = std::cos(w * dl);
+        car[2 * mm + 1] = std::sin(w * dl);
+        for (int e2 = 0; e2 < NE; e2++) {
+          const double pr = std::cos(ta.bohr[e2] * dl), pi = std::sin(ta.bohr[e2] * dl);
+          Tt[((size_t)mm * NE + e2) * 2] = pr * ta.Tr[0][e2] - pi * ta.Ti[0][e2];
+          Tt[((size_t)mm * NE + e2) * 2 + 1] = pr * ta.Ti[0][e2] + pi * ta.Tr[0][e2];
+        }
+      }
+      auto base_time = [&](int c) { return g.times[(size_t)2 * SMALL_CHUNK_STEPS * c]; };
+      const double t_first = base_time(0), t_last = base_time(n_chunks0 - 1);
+      for (int j = 0; j < d; j++) {
+        fs[2 * j] = std::cos(m->fe[j] * t_first);
+        fs[2 * j + 1] = -std::sin(m->fe[j] * t_first);
+        fe_[2 * j] = std::cos(m->fe[j] * t_last);
+        fe_[2 * j + 1] = std::sin(m->fe[j] * t_last);
+      }
+      std::vector<double> chunk((size_t)n_chunks0 * (2 + SMALL_MAXD) * 2, 0.0);
+      for (int c = 0; c < n_chunks0; c++) {
+        double* q = chunk.data() + (size_t)c * (2 + SMALL_MAXD) * 2;
+        const double t0c = base_time(c), dtc = c + 1 < n_chunks0 ? base_time(c + 1) - t0c : 0.0;
+        q[0] = std::cos(w * t0c);
+        q[1] = std::sin(w * t0c);
+        q[2] = std::cos(w * dtc);
+        q[3] = std::sin(w * dtc);
+        for (int j = 0; j < d; j++) {
+          q[4 + 2 * j] = std::cos(m->fe[j] * dtc);
+          q[5 + 2 * j] = -std::sin(m->fe[j] * dtc);
+        }
+      }
+      if ((rc = m->ct_chunk.ensure(chunk.size() * sizeof(double)))) return rc;
+      // 21 kB for the headline grid, once per cache miss: the runtime stages a pageable source of this size before returning
+      CASQ_CUDA(cudaMemcpyAsync(m->ct_chunk.p, chunk.data(), chunk.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     // the host vectors above are pageable: the async copies have been staged by the runtime on return
     m->tab_key = key;
   }
@@ -1039,6 +1180,10 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     const double per_sm = (double)grid / sms;
     bool sliced = m->tab_n_pieces == 1 && grid > (unsigned)sms && n_chunks0 >= 32 && std::fabs(per_sm - std::round(per_sm)) > 0.02;
     if (const char* env = getenv("CASQ_SMALL_SLICED")) sliced = atoi(env) != 0 && m->tab_n_pieces == 1 && n_chunks0 >= 2;
+    // constant-table variant: one piece, and the offset table was built with the grid (see the cache-miss branch)
+    const int NE2 = tri ? d - 1 : d * (d - 1) / 2;
+    const bool use_ct = m->tab_n_pieces == 1 && m->small_ct.size() == (size_t)2 * kEnt + (size_t)2 * kEnt * NE2 + 4 * SMALL_MAXD &&
+                        !getenv("CASQ_SMALL_NO_CONST_TABLE");
     SliceCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
     if (sliced) {
@@ -1059,24 +1204,49 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
       ctl.state = (double*)(sb + o_state);
       sv_small2_slice_init_kernel<<<(ctl.total + 255) / 256, 256, 0, st>>>(ctl);
     }
-#define LAUNCH2(D_, T_)                                                                                                    \
+#define LAUNCH2K(D_, T_, C_, CTARG)                                                                                         \
   {                                                                                                                        \
-    const size_t smem2 = 2 * (size_t)kEnt * Entry<D_, 1, false, false, T_>::W * sizeof(double);                            \
+    const size_t smem2 = C_ ? 0 : 2 * (size_t)kEnt * Entry<D_, 1, false, false, T_>::W * sizeof(double);                   \
     if (sliced) {                                                                                                          \
-      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, true, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
       int nb = 0;                                                                                                          \
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv_rk4_small2_kernel<D_, T_, true>, block, smem2); \
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sv_rk4_small2_kernel<D_, T_, true, C_>, block, smem2); \
       if (e == cudaSuccess) {                                                                                              \
         const unsigned workers = (unsigned)std::max(1, nb) * (unsigned)sms; /* every resident block slot */                \
-        sv_rk4_small2_kernel<D_, T_, true><<<workers, block, smem2, st>>>(a, ctl);                                         \
+        sv_rk4_small2_kernel<D_, T_, true, C_><<<workers, block, smem2, st>>>(a, ctl, CTARG);                              \
         e = cudaGetLastError();                                                                                            \
       }                                                                                                                    \
     } else {                                                                                                               \
-      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+      e = cudaFuncSetAttribute(sv_rk4_small2_kernel<D_, T_, false, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
       if (e == cudaSuccess) {                                                                                              \
-        sv_rk4_small2_kernel<D_, T_, false><<<grid, block, smem2, st>>>(a, ctl);                                           \
+        sv_rk4_small2_kernel<D_, T_, false, C_><<<grid, block, smem2, st>>>(a, ctl, CTARG);                                \
         e = cudaGetLastError();                                                                                            \
       }                                                                                                                    \
+    }                                                                                                                      \
+  }
+#define LAUNCH2(D_, T_)                                                                                                    \
+  {                                                                                                                        \
+    if (use_ct) {                                                                                                          \
+      constexpr int NE_ = Couplings<D_, T_>::NE;                                                                           \
+      ConstTab<NE_> ctab;                                                                                                  \
+      memset(&ctab, 0, sizeof(ctab));                                                                                      \
+      const double* v = m->small_ct.data();                                                                                \
+      for (int mm = 0; mm < kEnt; mm++) {                                                                                  \
+        ctab.car[mm] = make_double2(v[2 * mm], v[2 * mm + 1]);                                                             \
+        for (int e2 = 0; e2 < NE_; e2++)                                                                                   \
+          ctab.T[mm][e2] = make_double2(v[2 * kEnt + ((size_t)mm * NE_ + e2) * 2], v[2 * kEnt + ((size_t)mm * NE_ + e2) * 2 + 1]); \
+      }                                                                                                                    \
+      const double* fs = v + 2 * kEnt + (size_t)2 * kEnt * NE_;                                                            \
+      for (int j = 0; j < SMALL_MAXD; j++) {                                                                               \
+        ctab.f_start[j] = make_double2(fs[2 * j], fs[2 * j + 1]);                                                          \
+        ctab.f_end[j] = make_double2(fs[2 * SMALL_MAXD + 2 * j], fs[2 * SMALL_MAXD + 2 * j + 1]);                          \
+      }                                                                                                                    \
+      ctab.chunk = (const double2*)m->ct_chunk.p;                                                                          \
+      LAUNCH2K(D_, T_, true, ctab)                                                                                         \
+    } else {                                                                                                               \
+      NoConstTab none;                                                                                                     \
+      none.unused = 0;                                                                                                     \
+      LAUNCH2K(D_, T_, false, none)                                                                                        \
     }                                                                                                                      \
   }
     if (d == 2) LAUNCH2(2, true)
@@ -1085,6 +1255,7 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     else if (tri) LAUNCH2(4, true)
     else LAUNCH2(4, false)
 #undef LAUNCH2
+#undef LAUNCH2K
   } else {
     e = dispatch_small(d, KA, m->rwa, has_s, tri, a, st);
   }

@@ -34,6 +34,48 @@ __global__ void __launch_bounds__(64) k(double* out, const double* in, int iters
   out[blockIdx.x * 64 + threadIdx.x] = s;
 }
 
+// MODE 3: the multiplicand comes from a table passed as a kernel PARAMETER (constant bank -> LDCU -> uniform register
+// operand of the DFMA), the other two operands are distinct vector registers
+struct ParamTab { double t[512]; };
+__global__ void __launch_bounds__(64) kparam(double* out, const double* in, const ParamTab p, int iters) {
+  double acc[12], x[8];
+  for (int i = 0; i < 12; i++) acc[i] = in[threadIdx.x + 64 * i];
+  for (int i = 0; i < 8; i++) x[i] = in[threadIdx.x + 64 * (12 + i)];
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double c = p.t[(it * 4 + r) & 511];
+#pragma unroll
+      for (int i = 0; i < 12; i++) acc[i] = fma(c, x[(i + r) & 7], acc[i]);
+    }
+  }
+  double s = 0;
+  for (int i = 0; i < 12; i++) s += acc[i];
+  out[blockIdx.x * 64 + threadIdx.x] = s;
+}
+void run_param(int blocks_per_sm, double* out, double* in) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int iters = 20000;
+  ParamTab p;
+  for (int i = 0; i < 512; i++) p.t[i] = 1e-9 * i;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  kparam<<<sms * blocks_per_sm, 64>>>(out, in, p, 100);
+  cudaEventRecord(e0);
+  kparam<<<sms * blocks_per_sm, 64>>>(out, in, p, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  int clk = 0;
+  cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  const double warps_per_smsp = blocks_per_sm * 2 / 4.0;
+  printf("%-44s warps/SMSP %.1f: %.3f ms, %.2f cycles per fp64 instruction per SMSP\n", "multiplicand from a kernel parameter (UR)", warps_per_smsp, ms,
+         ms * 1e-3 * clk * 1e3 / ((double)iters * 48 * warps_per_smsp));
+}
+
 template <int MODE>
 void run(const char* name, int blocks_per_sm, double* out, double* in) {
   int sms = 148;
@@ -67,6 +109,7 @@ int main() {
     run<0>("invariant multiplicands", b, out, in);
     run<1>("distinct register operands", b, out, in);
     run<2>("operands from other chains + DMUL stream", b, out, in);
+    run_param(b, out, in);
   }
   return 0;
 }

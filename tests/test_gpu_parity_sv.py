@@ -429,20 +429,36 @@ def test_rk4_two_per_thread_kernel_is_bit_identical_to_one_per_thread(case, monk
         _, want = O.rk4_solve(om, samples, y0[idx], span, DT / 40, te)
         assert np.abs(auto.cpu().numpy()[idx] - want).max() < TOL_STATE
         # one piece (no t_eval): B = 1e5 takes the TIME-SLICED persistent kernel (782 blocks do not divide over 148 SMs).
-        # Sliced, unsliced and one-trajectory-per-thread runs must agree bit for bit, for two segment lengths.
-        runs = {}
-        for tag, env in (("sliced4", {"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "4"}),
-                         ("sliced7", {"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "7"}),
-                         ("unsliced", {"CASQ_SMALL_SLICED": "0"}), ("one", {"CASQ_SMALL_TRAJ_PER_THREAD": "1"}), ("default", {})):
+        # With the stage table in shared memory (CASQ_SMALL_NO_CONST_TABLE) sliced, unsliced and one-trajectory-per-thread
+        # runs must agree bit for bit, for two segment lengths.
+        def run(env):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             nm.invalidate_cache()
-            runs[tag] = engine.solve_sv_rk4(nm, slots, params, y0, span, DT / 40).clone()
+            r = engine.solve_sv_rk4(nm, slots, params, y0, span, DT / 40).clone()
             torch.cuda.synchronize()
             for k in env:
                 monkeypatch.delenv(k)
-        for tag in ("sliced7", "unsliced", "one", "default"):
+            return r
+
+        tab = {"CASQ_SMALL_NO_CONST_TABLE": "1"}
+        runs = {"sliced4": run({**tab, "CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "4"}),
+                "sliced7": run({**tab, "CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "7"}),
+                "unsliced": run({**tab, "CASQ_SMALL_SLICED": "0"}), "one": run({"CASQ_SMALL_TRAJ_PER_THREAD": "1"}),
+                "table-default": run(tab)}
+        for tag in ("sliced7", "unsliced", "one", "table-default"):
             assert torch.equal(runs["sliced4"], runs[tag]), (case[0], B, tag)
+        # The default is the CONSTANT-TABLE variant (offset table in the constant bank, state carried in the frame of the
+        # current 32-step chunk): the same RK4 in a constant diagonal change of variables per chunk, so it agrees with the
+        # table kernel to rounding (not bit for bit), with itself bit for bit whatever the slicing, and with the oracle.
+        ct = {"ct-sliced4": run({"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "4"}),
+              "ct-sliced7": run({"CASQ_SMALL_SLICED": "1", "CASQ_SMALL_SLICE_CHUNKS": "7"}),
+              "ct-unsliced": run({"CASQ_SMALL_SLICED": "0"}), "default": run({})}
+        for tag in ("ct-sliced7", "ct-unsliced", "default"):
+            assert torch.equal(ct["ct-sliced4"], ct[tag]), (case[0], B, tag)
+        assert float((ct["default"] - runs["sliced4"]).abs().max()) < 1e-12, (case[0], B)
+        _, want1 = O.rk4_solve(om, samples, y0[idx], span, DT / 40)
+        assert np.abs(ct["default"].cpu().numpy()[idx] - want1).max() < TOL_STATE
 
 
 def test_cfg5_dopri5_256_candidates_against_oracle_and_truth():
