@@ -604,7 +604,7 @@ def run_ours(args) -> None:
             "gpu_launches": 3 * args.steps,  # per step: stage-table kernel, slice-queue init kernel, RK4 kernel
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
-                         "kernel": "sv_rk4_small2_kernel<3,TRI,SLICED> (2 trajectories per thread, time-sliced persistent grid)", "kernel_ms": ms_kernel,
+                         "kernel": "sv_rk4_small2_kernel<3,TRI,SLICED,CT> (2 trajectories per thread, time-sliced persistent grid, offset table in the constant bank)", "kernel_ms": ms_kernel,
                          "flop_per_step": FLOP_PER_STEP, "dense_model_flop_per_step": FLOP_PER_STEP_DENSE_MODEL,
                          "peak_source": "measured live: casq_fp64_fma_probe (MEASURED_PEAKS.json has no fp64 entry)"},
             "cpu_baseline": cpu,
