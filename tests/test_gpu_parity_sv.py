@@ -461,6 +461,33 @@ def test_rk4_two_per_thread_kernel_is_bit_identical_to_one_per_thread(case, monk
         assert np.abs(ct["default"].cpu().numpy()[idx] - want1).max() < TOL_STATE
 
 
+@pytest.mark.parametrize("span_samples", [(0.0, 0.6), (3.0, 20.5), (7.25, 48.0)])
+def test_rk4_constant_table_variant_spans(span_samples, monkeypatch):
+    """The constant-table variant of the two-trajectory kernel on spans that do not start at t = 0 (the frame of chunk 0 is
+    not the rotating frame then), that end inside a chunk, and on a span of a single chunk: equal to the shared-memory-table
+    kernel to rounding and to the oracle on a few points."""
+    om, nm, ch = _models((0,), "full")
+    rng = np.random.default_rng(5)
+    B, dur = 16400, 48
+    p = dict(amp=rng.uniform(0.05, 0.9, B), angle=rng.uniform(-np.pi, np.pi, B), sigma=rng.uniform(5, 20, B), beta=rng.uniform(-3, 3, B))
+    params = engine.pack_params([p], device="cuda")
+    y0 = rng.normal(size=(B, 3)) + 1j * rng.normal(size=(B, 3))
+    y0 /= np.linalg.norm(y0, axis=1, keepdims=True)
+    span = (span_samples[0] * DT, span_samples[1] * DT)
+    slots = [("drag", 0, 0, dur)]
+    nm.invalidate_cache()
+    got = engine.solve_sv_rk4(nm, slots, params, y0, span, DT / 40).clone()
+    monkeypatch.setenv("CASQ_SMALL_NO_CONST_TABLE", "1")
+    nm.invalidate_cache()
+    ref = engine.solve_sv_rk4(nm, slots, params, y0, span, DT / 40).clone()
+    assert float((got - ref).abs().max()) < 1e-12
+    assert torch.equal(got[:, 0], ref[:, 0])  # the initial state is written before any frame change
+    idx = np.array([0, 1, B // 2, B - 1])
+    samples = O.channel_samples(ch, [O.PulseSpec("drag", "d0", dur)], [{k: v[idx] for k, v in p.items()}])
+    _, want = O.rk4_solve(om, samples, y0[idx], span, DT / 40)
+    assert np.abs(got.cpu().numpy()[idx] - want).max() < TOL_STATE
+
+
 def test_cfg5_dopri5_256_candidates_against_oracle_and_truth():
     """BASELINE cfg 5 settings (DRAG duration 256, amp 0.12, (sigma, beta) ~ U[16,128] x U[-4,4], hmax = dt) on 256
     candidates against the oracle's jax-odeint restatement AND a tight-tolerance DOP853 truth.
