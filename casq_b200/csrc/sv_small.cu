@@ -1182,8 +1182,11 @@ int casq_small_rk4(casq_model* m, int KA, const int* active, const DevSlots& slo
     if (const char* env = getenv("CASQ_SMALL_SLICED")) sliced = atoi(env) != 0 && m->tab_n_pieces == 1 && n_chunks0 >= 2;
     // constant-table variant: one piece, and the offset table was built with the grid (see the cache-miss branch)
     const int NE2 = tri ? d - 1 : d * (d - 1) / 2;
+    // (its parameter block is 3.5 - 7.5 kB: kernel parameters beyond 4 kB need a CUDA 12.1 driver)
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
     const bool use_ct = m->tab_n_pieces == 1 && m->small_ct.size() == (size_t)2 * kEnt + (size_t)2 * kEnt * NE2 + 4 * SMALL_MAXD &&
-                        !getenv("CASQ_SMALL_NO_CONST_TABLE");
+                        drv >= 12010 && !getenv("CASQ_SMALL_NO_CONST_TABLE");
     SliceCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
     if (sliced) {
