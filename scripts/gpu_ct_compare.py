@@ -1,3 +1,5 @@
+"""Headline sweep (1e5 points, S = 10 280) solved by the constant-table and by the shared-memory-table variant of
+sv_rk4_small2_kernel: prints the largest difference between the two.  Usage: python scripts/gpu_ct_compare.py"""
 import sys, os; sys.path.insert(0, ".")
 import numpy as np, torch
 from casq_b200 import engine
