@@ -16,6 +16,9 @@
 //    changes -- once per ~40 steps -- from the per-point parameters (amp, angle, sigma, width, beta).
 //  * operator sparsity is a compile-time property of the instantiation (TRI = tridiagonal ladder coupling,
 //    HAS_S = static/diagonal terms survive in the frame), so absent elements cost neither registers nor flops.
+//  * large batches of the headline shape run sv_rk4_small2_kernel: two trajectories per thread, a persistent grid
+//    that hands jobs over between SMs (SliceCtl), and -- for one piece -- the table's offset part in the constant
+//    bank so that the couplings reach the DFMAs as uniform-register operands (ConstTab).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -43,7 +46,7 @@ struct SmallArgs {
   int n_pieces;
   long long B;
   int T;
-  const double* params;  // SoA [n_slots][5][B]
+  const double* params;  // SoA [n_slots][CASQ_NPARAM][B]
   const double* y0;      // lab basis
   int y0_batched;
   double* out;  // [B][T][D] c128
